@@ -1,0 +1,167 @@
+/*
+ * vidar_b200.h -- C ABI of libvidar_b200.so: the B200 (sm_100a) kernels that sit
+ * under ViDAR's two hot-path operator boundaries.
+ *
+ *   (i)  multi-scale deformable attention   (mmcv `_ext.ms_deform_attn_{forward,backward}`,
+ *        bound at projects/mmdet3d_plugin/bevformer/modules/multi_scale_deformable_attn_function.py:10-12,
+ *        called at :42-48, :74-84, :118-124, :150-160)
+ *   (ii) the voxel ray-caster family        (third_lib/dvr/dvr.cpp:65-69, third_lib/dvxlr/dvxlr.cpp:61-65,
+ *        third_lib/dvxlr/dvxlr_v2.cpp:67-70) and the in-model renderers built on the same
+ *        volume (latent_rendering.py:79-162, vidar_head_base.py:420-509,586-592,662-752).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a dense, contiguous, 16-byte aligned buffer
+ *     unless the parameter name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     no entry point synchronises the device or allocates memory;
+ *   - return value 0 = success, non-zero = VIDAR_E_* ; vidar_last_error() gives the
+ *     message of the last failure on the calling thread (the Python layer turns it
+ *     into RuntimeError/ValueError, the reference raises through TORCH_CHECK);
+ *   - all floating-point I/O is fp32 (the reference casts to fp32 with
+ *     custom_fwd(cast_inputs=torch.float32), multi_scale_deformable_attn_function.py:93;
+ *     the ray-casters are dispatched on float tensors, dvr.cu:367).
+ *
+ * No torch types appear here: the library links only against libcudart.
+ */
+#ifndef VIDAR_B200_H_
+#define VIDAR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  VIDAR_OK = 0,
+  VIDAR_E_INVALID = 1,   /* bad argument (shape, null pointer, unknown enum) */
+  VIDAR_E_CUDA = 2,      /* a CUDA runtime call or launch failed */
+  VIDAR_E_UNSUPPORTED = 3
+};
+
+/* Message of the last error raised on this thread ("" if none). */
+const char* vidar_last_error(void);
+/* Library / build identification, e.g. "vidar_b200 0.1 sm_100a". */
+const char* vidar_version(void);
+/* Number of kernels this library has launched since load (all threads).  bench.py
+ * reports the delta across the timed region as `gpu_launches`. */
+int64_t vidar_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * (i) Multi-scale deformable attention
+ * ---------------------------------------------------------------------------------- */
+
+/* Replaces ext_module.ms_deform_attn_forward
+ *   (multi_scale_deformable_attn_function.py:118-124).
+ *   value            [B, K, H, C]        K = sum_l Hl*Wl
+ *   spatial_shapes   [L, 2] int64 (h, w) (device)
+ *   level_start      [L]    int64        (device)
+ *   sampling_loc     [B, Q, H, L, P, 2]  (x, y) normalised to [0,1]
+ *   attn_weight      [B, Q, H, L, P]
+ *   out              [B, Q, H*C]         fully overwritten
+ * im2col_step is validated like mmcv (B % min(B, im2col_step) == 0) and otherwise unused. */
+int vidar_msda_forward(const float* value, const int64_t* spatial_shapes,
+                       const int64_t* level_start, const float* sampling_loc,
+                       const float* attn_weight, float* out,
+                       int B, int K, int H, int C, int L, int Q, int P,
+                       int im2col_step, void* stream);
+
+/* Replaces ext_module.ms_deform_attn_backward
+ *   (multi_scale_deformable_attn_function.py:150-160).
+ *   grad_out          [B, Q, H*C]
+ *   grad_value        [B, K, H, C]        accumulated with atomics: caller zeroes it
+ *                                         (torch.zeros_like, :146)
+ *   grad_sampling_loc [B, Q, H, L, P, 2]  fully overwritten
+ *   grad_attn_weight  [B, Q, H, L, P]     fully overwritten                              */
+int vidar_msda_backward(const float* value, const int64_t* spatial_shapes,
+                        const int64_t* level_start, const float* sampling_loc,
+                        const float* attn_weight, const float* grad_out,
+                        float* grad_value, float* grad_sampling_loc,
+                        float* grad_attn_weight,
+                        int B, int K, int H, int C, int L, int Q, int P,
+                        int im2col_step, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (ii-a) dvr / dvxlr / dvxlr_v2 voxel ray-casters
+ *   sigma   [N, T, Z, Y, X]   (reference names the dims H, L, W)
+ *   origin  [N, T, 3]         voxel units (x, y, z)
+ *   points  [N, M, 3]         voxel units (x, y, z), NaN for padded rays
+ *   tindex  [N, M]            FLOAT frame index, < 0 = padded ray (skipped)
+ *   T  = sigma frames, To = origin frames (origin is indexed by t, sigma by
+ *        ts = (T == 1) ? 0 : t, dvr.cu:97,109)
+ * ---------------------------------------------------------------------------------- */
+
+/* dvr.init / dvxlr.init (dvr.cu:14-63,705-738; dvxlr.cu:12-61,528-561).
+ *   occupancy [N, T, Z, Y, X]  caller zeroes it; set to 1 at every ray end point. */
+int vidar_dvr_init(const float* points, const float* tindex, float* occupancy,
+                   int N, int M, int T, int Z, int Y, int X, void* stream);
+
+/* dvr.render_forward (dvr.cu:65-317,327-383).  train_phase: 0 = "test", 1 = "train".
+ *   pred_dist, gt_dist [N, M]  caller fills with -1 (dvr.cu:354-355); rays that never
+ *   enter the grid keep it. */
+int vidar_dvr_render_forward(const float* sigma, const float* origin, const float* points,
+                             const float* tindex, float* pred_dist, float* gt_dist,
+                             int N, int M, int T, int To, int Z, int Y, int X,
+                             int train_phase, void* stream);
+
+/* dvr.render (dvr.cu:385-627,639-694): forward + loss gradient in one call.
+ *   loss_type: 0 = "l1" (also "bce", dvr.cu:667-668), 1 = "l2", 2 = "absrel".
+ *   grad_sigma [N, T, Z, Y, X]  caller zeroes it; accumulated atomically (the
+ *   reference's `+=` at dvr.cu:622 is a documented race; this is the race-free sum). */
+int vidar_dvr_render(const float* sigma, const float* origin, const float* points,
+                     const float* tindex, float* pred_dist, float* gt_dist,
+                     float* grad_sigma, int N, int M, int T, int To, int Z, int Y, int X,
+                     int loss_type, void* stream);
+
+/* dvxlr.render (dvxlr.cu:160-517) and dvxlr_v2.render_v2 (dvxlr_v2.cu:119-493).
+ *   max_d                  third dim of the list outputs (reference: 1026, dvxlr.cu:10)
+ *   dd_dsigma [N, M, max_d]      caller zeroes            (dvxlr.cu:492)
+ *   indices   [N, M, max_d, 3]   caller zeroes; (z, y, x) stored as float (dvxlr.cu:450-452)
+ *   (dd_dsigma and indices may both be NULL: the lists are then not written -- used by
+ *    the fused autograd path, which never needs them)
+ *   v2 only (pass NULL for v1):
+ *   sigma_regul [N, T, Z, Y, X]
+ *   ray_pred  [N, M, max_d]      caller zeroes            (dvxlr_v2.cu:467)
+ *   indicator [N, M, max_d]      caller fills with -1     (dvxlr_v2.cu:468)               */
+int vidar_dvxlr_render(const float* sigma, const float* origin, const float* points,
+                       const float* tindex, const float* sigma_regul,
+                       float* pred_dist, float* gt_dist, float* dd_dsigma, float* indices,
+                       float* ray_pred, float* indicator,
+                       int N, int M, int T, int To, int Z, int Y, int X, int max_d,
+                       void* stream);
+
+/* Forward half of DifferentiableVoxelRendering without the lists: pred_dist / gt_dist
+ * only (both caller-filled with -1), same traversal as dvxlr.render. */
+int vidar_dvxlr_forward(const float* sigma, const float* origin, const float* points,
+                        const float* tindex, float* pred_dist, float* gt_dist,
+                        int N, int M, int T, int To, int Z, int Y, int X, void* stream);
+
+/* dvxlr.get_grad_sigma (dvxlr.cu:63-156) and dvxlr_v2.get_grad_sigma_v2 (dvxlr_v2.cu:12-115).
+ *   elementwise_mult [N, M, max_d]; indices [N, M, max_d, 3]
+ *   grad_sigma [N, T, Z, Y, X] caller zeroes.
+ *   v2 only (NULL for v1): indicator, grad_ray_pred [N, M, max_d]; grad_sigma_regul like
+ *   grad_sigma, caller zeroes. */
+int vidar_dvxlr_get_grad_sigma(const float* elementwise_mult, const float* indices,
+                               const float* tindex, const float* indicator,
+                               const float* grad_ray_pred, float* grad_sigma,
+                               float* grad_sigma_regul,
+                               int N, int M, int T, int Z, int Y, int X, int max_d,
+                               void* stream);
+
+/* Fused backward of DifferentiableVoxelRendering[V2] (e2e_predictor_utils.py:91-143):
+ * re-walks every ray and scatters grad_pred[n,m] * d pred/d sigma straight into
+ * grad_sigma -- the [N,M,1026(,3)] lists are never materialised.  Same result as
+ * dvxlr.render + `gradpred[...,None]*dd_dsigma` (NaN -> 0, :104-108) + get_grad_sigma.
+ *   grad_pred [N, M];  grad_sigma caller-zeroed.
+ *   v2 only (NULL otherwise): grad_ray_pred [N, M, max_d] -> grad_sigma_regul. */
+int vidar_dvxlr_backward_fused(const float* sigma, const float* origin, const float* points,
+                               const float* tindex, const float* grad_pred,
+                               const float* grad_ray_pred, float* grad_sigma,
+                               float* grad_sigma_regul,
+                               int N, int M, int T, int To, int Z, int Y, int X, int max_d,
+                               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDAR_B200_H_ */

@@ -1,0 +1,94 @@
+"""Compile the reference's OWN ray-caster kernels for sm_100a into oracle/_ref/ (git-ignored).
+
+TEST INFRASTRUCTURE.  third_lib/dvr and third_lib/dvxlr are torch C++/CUDA extensions made
+of two files each; they are compiled from where they lie under /root/reference by this
+recipe, never copied into the repo.  They do not build unmodified against torch 2.11
+(`AT_DISPATCH_FLOATING_TYPES(x.type(), ...)` needs a ScalarType; `x.type().is_cuda()` is
+gone), so the recipe applies a mechanical two-token patch to a *temporary* copy:
+    .type().is_cuda()  ->  .is_cuda()
+    X.type(),          ->  X.scalar_type(),     (inside AT_DISPATCH_FLOATING_TYPES only)
+No arithmetic is touched.  Outputs: oracle/_ref/ref_{dvr,dvxlr,dvxlr_v2}.so.
+
+The products can only *run* on a GPU box.  They serve as (1) a second oracle there
+(tests/test_ref_cuda_gpu.py, tools/make_golden_dvr.py) and (2) the same-box GPU baseline.
+/root/reference does not exist on the GPU box: build here, the .so files travel.
+"""
+import os
+import re
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+REF = "/root/reference/third_lib"
+TARGETS = {
+    "ref_dvr": ("dvr", ["dvr.cpp", "dvr.cu"]),
+    "ref_dvxlr": ("dvxlr", ["dvxlr.cpp", "dvxlr.cu"]),
+    "ref_dvxlr_v2": ("dvxlr", ["dvxlr_v2.cpp", "dvxlr_v2.cu"]),
+}
+
+
+def _patch(text):
+    text = text.replace(".type().is_cuda()", ".is_cuda()")
+    text = re.sub(r"AT_DISPATCH_FLOATING_TYPES\((\w+)\.type\(\)", r"AT_DISPATCH_FLOATING_TYPES(\1.scalar_type()", text)
+    return text
+
+
+def so_path(name):
+    return os.path.join(OUT, name + ".so")
+
+
+def build(names=None, force=False):
+    if not os.path.isdir(REF):
+        return {}        # GPU box: use the prebuilt files
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    os.environ.setdefault("MAX_JOBS", "4")
+    from torch.utils import cpp_extension
+    os.makedirs(OUT, exist_ok=True)
+    built = {}
+    for name, (sub, files) in TARGETS.items():
+        if names and name not in names:
+            continue
+        if os.path.exists(so_path(name)) and not force:
+            built[name] = so_path(name)
+            continue
+        tmp = tempfile.mkdtemp(prefix=f"{name}_src_")
+        bdir = tempfile.mkdtemp(prefix=f"{name}_build_")
+        try:
+            srcs = []
+            for f in files:
+                with open(os.path.join(REF, sub, f)) as fh:
+                    text = _patch(fh.read())
+                dst = os.path.join(tmp, f)
+                with open(dst, "w") as fh:
+                    fh.write(text)
+                srcs.append(dst)
+            cpp_extension.load(
+                name=name, sources=srcs, build_directory=bdir, verbose=False,
+                extra_cuda_cflags=["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"],
+                is_python_module=False)
+            shutil.copy(os.path.join(bdir, name + ".so"), so_path(name))
+            built[name] = so_path(name)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+            shutil.rmtree(bdir, ignore_errors=True)
+    return built
+
+
+def load(name):
+    """Import a prebuilt reference extension (needs a CUDA-capable torch at call time)."""
+    import importlib.util
+
+    import torch  # noqa: F401  (libtorch must be loaded before the extension)
+    path = so_path(name)
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} not built (run `python oracle/build_ref.py` where /root/reference exists)")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+if __name__ == "__main__":
+    print(build(names=sys.argv[1:] or None, force=False))

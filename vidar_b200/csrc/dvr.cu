@@ -1,0 +1,592 @@
+// Voxel ray-casters (dvr / dvxlr / dvxlr_v2) for B200 (sm_100a).
+//
+// Reference: third_lib/dvr/dvr.cu (init :14-63, render_forward :65-317, render :385-627),
+// third_lib/dvxlr/dvxlr.cu (render :160-457, get_grad_sigma :63-112),
+// third_lib/dvxlr/dvxlr_v2.cu (indicator / ray_pred :408-423, second scatter :62-64).
+//
+// What is kept bit-for-bit: the Amanatides-Woo traversal in fp64 with the reference's
+// operation order (float->int truncation of the origin, the -1:+1 / 0:+1 first-boundary
+// rule, strict-< tie order X<Y, X<Z, Y<Z else Z, the rounded "path" voxel of
+// render_forward/dvxlr, the consecutive-duplicate merge of dvxlr, termination rules),
+// so every branch decision equals the reference's.
+//
+// What is redesigned: the reference keeps five MAX_D-long fp64/int3 arrays per thread
+// (52-75 KB of local memory per ray, dvr.cu:176-179,490-494,594) and walks them three
+// times.  Here a ray is a register-only stream:
+//     T_i = exp(-csd_i),  Delta_i = d_{i+1} - d_i
+//     pred      = sum_i (T_{i-1} - T_i) d_i + T_last d_last          (same order as ref)
+//     dpred/dsigma_j = -dt_j * (S_0 - R_j),   R_j = sum_{k<j} T_k Delta_k,  S_0 = R_last
+// (identical to the D_i recursion at dvr.cu:595-608).  The gradient needs
+// S_0 before the first emission, so gradient kernels walk the ray twice (pass 1: pred,
+// S_0; pass 2: emit) instead of storing the path.  Gradients are accumulated with
+// red.global.add.f32 (the reference's `+=` at dvr.cu:622 is a data race).
+// Launch: 64-thread blocks (30k rays -> 469 blocks over 148 SMs; the reference's
+// 1024-thread blocks give 30 blocks), one ray per thread, neighbouring rays in a warp.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace vidar {
+namespace {
+
+enum Variant { V_DVR_FWD = 0, V_DVR_RENDER = 1, V_DVXLR = 2 };
+
+template <int V> struct Traits;
+template <> struct Traits<V_DVR_FWD>    { static constexpr bool kRounded = true;  static constexpr bool kMerge = false; static constexpr int kNegBoundary = -1; };
+template <> struct Traits<V_DVR_RENDER> { static constexpr bool kRounded = false; static constexpr bool kMerge = false; static constexpr int kNegBoundary = 0; };
+template <> struct Traits<V_DVXLR>      { static constexpr bool kRounded = true;  static constexpr bool kMerge = true;  static constexpr int kNegBoundary = -1; };
+
+struct Grid {
+  int N, M, T, To, Z, Y, X;
+};
+
+struct Ray {
+  double xo, yo, zo, dx, dy, dz, gt_d;
+  int vx0, vy0, vz0;
+  int n, ts;
+  bool ok;
+};
+
+__device__ __forceinline__ Ray load_ray(const Grid& G, const float* __restrict__ origin,
+                                        const float* __restrict__ points,
+                                        const float* __restrict__ tindex, int n, int c) {
+  Ray r;
+  r.ok = false;
+  r.n = n;
+  const float tf = tindex[(size_t)n * G.M + c];
+  if (tf < 0.f) return r;                      // padded ray (dvr.cu:100)
+  const int t = (int)tf;                       // float used as an index: truncation
+  if (t >= G.To) return r;                     // reference: out-of-bounds read
+  if (G.T != 1 && t >= G.T) return r;          // reference: device assert (dvr.cu:93)
+  r.ts = (G.T == 1) ? 0 : t;
+  const float* o = origin + ((size_t)n * G.To + t) * 3;   // origin indexed by t, not ts (:109)
+  const float* e = points + ((size_t)n * G.M + c) * 3;
+  r.xo = o[0]; r.yo = o[1]; r.zo = o[2];
+  const double xe = e[0], ye = e[1], ze = e[2];
+  r.vx0 = (int)r.xo; r.vy0 = (int)r.yo; r.vz0 = (int)r.zo;
+  const double rx = xe - r.xo, ry = ye - r.yo, rz = ze - r.zo;
+  r.gt_d = sqrt(rx * rx + ry * ry + rz * rz);
+  r.dx = rx / r.gt_d; r.dy = ry / r.gt_d; r.dz = rz / r.gt_d;
+  r.ok = true;
+  return r;
+}
+
+// The traversal loop shared by every kernel.  `visit(px,py,pz,_d,last_d)` is called for
+// each step taken while inside the grid, in order.
+template <int V, typename Visitor>
+__device__ __forceinline__ void walk(const Grid& G, const Ray& r, Visitor& visit) {
+  using TR = Traits<V>;
+  int vx = r.vx0, vy = r.vy0, vz = r.vz0;
+  double path_vx = (double)vx, path_vy = (double)vy, path_vz = (double)vz;
+  const int stepX = (r.dx >= 0) ? 1 : -1;
+  const int stepY = (r.dy >= 0) ? 1 : -1;
+  const int stepZ = (r.dz >= 0) ? 1 : -1;
+  const double nbx = vx + (stepX < 0 ? TR::kNegBoundary : 1);
+  const double nby = vy + (stepY < 0 ? TR::kNegBoundary : 1);
+  const double nbz = vz + (stepZ < 0 ? TR::kNegBoundary : 1);
+  double tMaxX = (r.dx != 0) ? (nbx - r.xo) / r.dx : DBL_MAX;
+  double tMaxY = (r.dy != 0) ? (nby - r.yo) / r.dy : DBL_MAX;
+  double tMaxZ = (r.dz != 0) ? (nbz - r.zo) / r.dz : DBL_MAX;
+  const double tDeltaX = (r.dx != 0) ? stepX / r.dx : DBL_MAX;
+  const double tDeltaY = (r.dy != 0) ? stepY / r.dy : DBL_MAX;
+  const double tDeltaZ = (r.dz != 0) ? stepZ / r.dz : DBL_MAX;
+  double last_d = 0.0;
+  bool was_inside = false;
+  // Safety net only: the reference loops forever on NaN directions that never enter
+  // the grid; every finite ray leaves within this many steps.
+  long long guard = 4LL * ((long long)G.X + G.Y + G.Z) + 64 +
+                    (long long)(fabs(r.xo) + fabs(r.yo) + fabs(r.zo)) * 2;
+  if (!(guard < (1LL << 24))) guard = 1LL << 24;
+  while (guard-- > 0) {
+    const bool inside = (0 <= vx && vx < G.X) && (0 <= vy && vy < G.Y) && (0 <= vz && vz < G.Z);
+    int px = vx, py = vy, pz = vz;
+    if (inside) {
+      was_inside = true;
+      if (TR::kRounded) {
+        px = (int)round(path_vx); px = px < G.X ? px : G.X - 1; px = px >= 0 ? px : 0;
+        py = (int)round(path_vy); py = py < G.Y ? py : G.Y - 1; py = py >= 0 ? py : 0;
+        pz = (int)round(path_vz); pz = pz < G.Z ? pz : G.Z - 1; pz = pz >= 0 ? pz : 0;
+      }
+    } else if (was_inside) {
+      break;
+    } else if (last_d > r.gt_d) {
+      break;
+    }
+    double _d;
+    if (tMaxX < tMaxY) {
+      if (tMaxX < tMaxZ) { _d = tMaxX; vx += stepX; tMaxX += tDeltaX; }
+      else               { _d = tMaxZ; vz += stepZ; tMaxZ += tDeltaZ; }
+    } else {
+      if (tMaxY < tMaxZ) { _d = tMaxY; vy += stepY; tMaxY += tDeltaY; }
+      else               { _d = tMaxZ; vz += stepZ; tMaxZ += tDeltaZ; }
+    }
+    if (TR::kRounded) {
+      const double adv = fmax(0.0, _d - last_d);
+      path_vx += adv * r.dx;
+      path_vy += adv * r.dy;
+      path_vz += adv * r.dz;
+    }
+    if (inside) visit(px, py, pz, _d, last_d);
+    last_d = _d;
+  }
+}
+
+// A committed segment: voxel, sigma there, length dt, exit distance d, index i.
+// Segmenter turns visits into segments, applying dvxlr's duplicate merge
+// (dvxlr.cu:366-373): a visit to the voxel of the pending segment extends it.
+template <bool MERGE, typename Sink>
+struct Segmenter {
+  const float* __restrict__ sig;  // sigma + (n*T + ts)*Z*Y*X
+  int Y, X;
+  Sink& sink;
+  bool has = false;
+  int px = 0, py = 0, pz = 0;
+  double psigma = 0, pdt = 0, pd = 0;
+  __device__ __forceinline__ Segmenter(const float* s, int Y_, int X_, Sink& k) : sig(s), Y(Y_), X(X_), sink(k) {}
+  __device__ __forceinline__ void operator()(int x, int y, int z, double _d, double last_d) {
+    if (MERGE) {
+      if (has && x == px && y == py && z == pz) {
+        const double start = last_d - pdt;       // last_d -= dt[count]
+        pdt = fmax(0.0, _d - start);
+        pd = _d;
+        return;
+      }
+      if (has) sink.commit(px, py, pz, psigma, pdt, pd);
+      has = true;
+      px = x; py = y; pz = z;
+      psigma = (double)__ldg(sig + ((size_t)z * Y + y) * X + x);
+      pdt = fmax(0.0, _d - last_d);
+      pd = _d;
+    } else {
+      const double s = (double)__ldg(sig + ((size_t)z * Y + y) * X + x);
+      sink.commit(x, y, z, s, fmax(0.0, _d - last_d), _d);
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    if (MERGE && has) sink.commit(px, py, pz, psigma, pdt, pd);
+  }
+};
+
+// Pass 1: expected distance, in the reference's summation order, plus S_0.
+struct Composite {
+  int count = 0;
+  double csd = 0.0, T_prev = 1.0, exp_d = 0.0, d_last = 0.0, S0 = 0.0;
+  __device__ __forceinline__ void commit(int, int, int, double sigma, double dt, double d) {
+    const double sd = sigma * dt;
+    const double csd_new = (count == 0) ? sd : csd + sd;
+    const double T_new = exp(-csd_new);
+    const double p = (count == 0) ? 1.0 - T_new : T_prev - T_new;
+    exp_d += p * d;
+    if (count > 0) S0 += T_prev * (d - d_last);
+    csd = csd_new;
+    T_prev = T_new;
+    d_last = d;
+    ++count;
+  }
+  // pred = sum p_i d_i + p_out * max_d   (dvr.cu:286-298)
+  __device__ __forceinline__ double pred() const { return exp_d + T_prev * d_last; }
+};
+
+// Pass 2 sinks.  All see segment i with R_i = sum_{k<i} T_k Delta_k and emit
+// dd_i = -dt_i (S0 - R_i).
+struct ScatterSink {  // atomically add coef * dd_i into grad_sigma
+  float* __restrict__ gsig;   // grad_sigma + frame offset
+  const float* __restrict__ grp;  // grad_ray_pred row for this ray (v2) or nullptr
+  float* __restrict__ gsreg;  // grad_sigma_regul + frame offset (v2) or nullptr
+  int Y, X, max_d;
+  double S0, coef;
+  bool nan_to_zero;
+  int count = 0;
+  double csd = 0.0, T_prev = 1.0, d_last = 0.0, R = 0.0;
+  __device__ __forceinline__ void commit(int x, int y, int z, double sigma, double dt, double d) {
+    if (count > 0) R += T_prev * (d - d_last);
+    const size_t vo = ((size_t)z * Y + y) * X + x;
+    if (count < max_d) {
+      // float(dd) * float(coef) like `gradpred[..., None] * dd_dsigma` on fp32 tensors
+      float g = (float)(-dt * (S0 - R)) * (float)coef;
+      if (nan_to_zero && isnan(g)) g = 0.f;
+      if (g != 0.f) red_add_f32(gsig + vo, g);
+      if (grp) {
+        const float gr = grp[count];
+        if (gr != 0.f) red_add_f32(gsreg + vo, gr);
+      }
+    }
+    const double sd = sigma * dt;
+    csd = (count == 0) ? sd : csd + sd;
+    T_prev = exp(-csd);
+    d_last = d;
+    ++count;
+  }
+};
+
+struct RenderGradSink {  // dvr.render: grad_sigma += dl_dd * dd_i in fp64 then fp32 atomics
+  float* __restrict__ gsig;
+  int Y, X;
+  double S0, dl_dd;
+  int count = 0;
+  double csd = 0.0, T_prev = 1.0, d_last = 0.0, R = 0.0;
+  __device__ __forceinline__ void commit(int x, int y, int z, double sigma, double dt, double d) {
+    if (count > 0) R += T_prev * (d - d_last);
+    const float g = (float)(dl_dd * (-dt * (S0 - R)));
+    if (g != 0.f) red_add_f32(gsig + ((size_t)z * Y + y) * X + x, g);
+    const double sd = sigma * dt;
+    csd = (count == 0) ? sd : csd + sd;
+    T_prev = exp(-csd);
+    d_last = d;
+    ++count;
+  }
+};
+
+struct ListSink {  // dvxlr.render: write the per-ray lists
+  float* __restrict__ dd;       // [max_d]
+  float* __restrict__ idx;      // [max_d,3]
+  float* __restrict__ ray_pred; // [max_d] or nullptr
+  float* __restrict__ indicator;
+  const float* __restrict__ sreg;  // sigma_regul + frame offset
+  int Y, X, max_d;
+  double S0, gt_raw;
+  bool reached = false;
+  int count = 0;
+  double csd = 0.0, T_prev = 1.0, d_last = 0.0, R = 0.0;
+  __device__ __forceinline__ void commit(int x, int y, int z, double sigma, double dt, double d) {
+    if (count > 0) R += T_prev * (d - d_last);
+    if (count < max_d) {
+      if (dd) {
+        dd[count] = (float)(-dt * (S0 - R));
+        idx[count * 3 + 0] = (float)z;
+        idx[count * 3 + 1] = (float)y;
+        idx[count * 3 + 2] = (float)x;
+      }
+      if (ray_pred) {
+        float ind = 0.f;
+        if (!reached && d >= gt_raw) { ind = 1.f; reached = true; }
+        indicator[count] = ind;
+        ray_pred[count] = __ldg(sreg + ((size_t)z * Y + y) * X + x);
+      }
+    }
+    const double sd = sigma * dt;
+    csd = (count == 0) ? sd : csd + sd;
+    T_prev = exp(-csd);
+    d_last = d;
+    ++count;
+  }
+};
+
+constexpr int kRayBlock = 64;
+
+__global__ void init_kernel(Grid G, const float* __restrict__ points,
+                            const float* __restrict__ tindex, float* __restrict__ occ) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= G.M) return;
+  const float tf = tindex[(size_t)n * G.M + c];
+  if (tf < 0.f) return;
+  const int t = (int)tf;
+  if (G.T != 1 && t >= G.T) return;
+  const int ts = (G.T == 1) ? 0 : t;
+  const float* e = points + ((size_t)n * G.M + c) * 3;
+  const int vx = (int)e[0], vy = (int)e[1], vz = (int)e[2];
+  if (0 <= vx && vx < G.X && 0 <= vy && vy < G.Y && 0 <= vz && vz < G.Z)
+    occ[((((size_t)n * G.T + ts) * G.Z + vz) * G.Y + vy) * G.X + vx] = 1.f;
+}
+
+// Forward only (dvr.render_forward; also the forward half of the fused autograd op).
+template <int V>
+__global__ void __launch_bounds__(kRayBlock)
+forward_kernel(Grid G, const float* __restrict__ sigma, const float* __restrict__ origin,
+               const float* __restrict__ points, const float* __restrict__ tindex,
+               float* __restrict__ pred_dist, float* __restrict__ gt_dist, int clamp_gt) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= G.M) return;
+  const Ray r = load_ray(G, origin, points, tindex, n, c);
+  if (!r.ok) return;
+  const size_t vol = (size_t)G.Z * G.Y * G.X;
+  Composite comp;
+  Segmenter<Traits<V>::kMerge, Composite> seg(sigma + ((size_t)n * G.T + r.ts) * vol, G.Y, G.X, comp);
+  walk<V>(G, r, seg);
+  seg.finish();
+  if (comp.count > 0) {
+    double gt = r.gt_d;
+    if (clamp_gt) gt = fmin(gt, comp.d_last);
+    pred_dist[(size_t)n * G.M + c] = (float)comp.pred();
+    gt_dist[(size_t)n * G.M + c] = (float)gt;
+  }
+}
+
+// dvr.render: forward + loss gradient (L1 / L2 / AbsRel), dvr.cu:576-625.
+__global__ void __launch_bounds__(kRayBlock)
+render_grad_kernel(Grid G, const float* __restrict__ sigma, const float* __restrict__ origin,
+                   const float* __restrict__ points, const float* __restrict__ tindex,
+                   float* __restrict__ pred_dist, float* __restrict__ gt_dist,
+                   float* __restrict__ grad_sigma, int loss_type) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= G.M) return;
+  const Ray r = load_ray(G, origin, points, tindex, n, c);
+  if (!r.ok) return;
+  const size_t vol = (size_t)G.Z * G.Y * G.X;
+  const size_t foff = ((size_t)n * G.T + r.ts) * vol;
+  Composite comp;
+  {
+    Segmenter<false, Composite> seg(sigma + foff, G.Y, G.X, comp);
+    walk<V_DVR_RENDER>(G, r, seg);
+  }
+  if (comp.count == 0) return;
+  const double exp_d = comp.pred();
+  const double gt = fmin(r.gt_d, comp.d_last);
+  pred_dist[(size_t)n * G.M + c] = (float)exp_d;
+  gt_dist[(size_t)n * G.M + c] = (float)gt;
+  double dl_dd = 1.0;
+  if (loss_type == 0) dl_dd = (exp_d >= gt) ? 1 : -1;
+  else if (loss_type == 1) dl_dd = (exp_d - gt);
+  else if (loss_type == 2) dl_dd = (exp_d >= gt) ? (1.0 / gt) : -(1.0 / gt);
+  RenderGradSink sink{grad_sigma + foff, G.Y, G.X, comp.S0, dl_dd};
+  Segmenter<false, RenderGradSink> seg(sigma + foff, G.Y, G.X, sink);
+  walk<V_DVR_RENDER>(G, r, seg);
+}
+
+// dvxlr.render / render_v2: forward + per-ray lists.
+__global__ void __launch_bounds__(kRayBlock)
+dvxlr_list_kernel(Grid G, const float* __restrict__ sigma, const float* __restrict__ origin,
+                  const float* __restrict__ points, const float* __restrict__ tindex,
+                  const float* __restrict__ sigma_regul, float* __restrict__ pred_dist,
+                  float* __restrict__ gt_dist, float* __restrict__ dd_dsigma,
+                  float* __restrict__ indices, float* __restrict__ ray_pred,
+                  float* __restrict__ indicator, int max_d) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= G.M) return;
+  const Ray r = load_ray(G, origin, points, tindex, n, c);
+  if (!r.ok) return;
+  const size_t vol = (size_t)G.Z * G.Y * G.X;
+  const size_t foff = ((size_t)n * G.T + r.ts) * vol;
+  Composite comp;
+  {
+    Segmenter<true, Composite> seg(sigma + foff, G.Y, G.X, comp);
+    walk<V_DVXLR>(G, r, seg);
+    seg.finish();
+  }
+  if (comp.count == 0) return;
+  const size_t ray = (size_t)n * G.M + c;
+  pred_dist[ray] = (float)comp.pred();
+  gt_dist[ray] = (float)fmin(r.gt_d, comp.d_last);
+  ListSink sink{dd_dsigma ? dd_dsigma + ray * max_d : nullptr,
+                indices ? indices + ray * max_d * 3 : nullptr,
+                ray_pred ? ray_pred + ray * max_d : nullptr,
+                indicator ? indicator + ray * max_d : nullptr,
+                sigma_regul ? sigma_regul + foff : nullptr, G.Y, G.X, max_d, comp.S0, r.gt_d};
+  Segmenter<true, ListSink> seg(sigma + foff, G.Y, G.X, sink);
+  walk<V_DVXLR>(G, r, seg);
+  seg.finish();
+}
+
+// Fused backward of DifferentiableVoxelRendering[V2]: no lists.
+__global__ void __launch_bounds__(kRayBlock)
+dvxlr_fused_bwd_kernel(Grid G, const float* __restrict__ sigma, const float* __restrict__ origin,
+                       const float* __restrict__ points, const float* __restrict__ tindex,
+                       const float* __restrict__ grad_pred, const float* __restrict__ grad_ray_pred,
+                       float* __restrict__ grad_sigma, float* __restrict__ grad_sigma_regul,
+                       int max_d) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= G.M) return;
+  const Ray r = load_ray(G, origin, points, tindex, n, c);
+  if (!r.ok) return;
+  const size_t vol = (size_t)G.Z * G.Y * G.X;
+  const size_t foff = ((size_t)n * G.T + r.ts) * vol;
+  Composite comp;
+  {
+    Segmenter<true, Composite> seg(sigma + foff, G.Y, G.X, comp);
+    walk<V_DVXLR>(G, r, seg);
+    seg.finish();
+  }
+  if (comp.count == 0) return;
+  const size_t ray = (size_t)n * G.M + c;
+  const bool v2 = grad_ray_pred != nullptr;
+  ScatterSink sink{grad_sigma + foff, v2 ? grad_ray_pred + ray * max_d : nullptr,
+                   v2 ? grad_sigma_regul + foff : nullptr, G.Y, G.X, max_d, comp.S0,
+                   (double)grad_pred[ray], !v2};
+  Segmenter<true, ScatterSink> seg(sigma + foff, G.Y, G.X, sink);
+  walk<V_DVXLR>(G, r, seg);
+  seg.finish();
+}
+
+// dvxlr.get_grad_sigma[_v2]: one warp per ray, lanes stride over the list so reads are
+// coalesced.  Exact zeros are skipped: the reference adds the zero padding of all
+// 1026 slots to voxel (0,0,0) (dvxlr.cu:101-110), which changes nothing but serialises
+// ~25M atomics on one address.
+__global__ void __launch_bounds__(256)
+list_scatter_kernel(Grid G, const float* __restrict__ em, const float* __restrict__ indices,
+                    const float* __restrict__ tindex, const float* __restrict__ indicator,
+                    const float* __restrict__ grad_ray_pred, float* __restrict__ grad_sigma,
+                    float* __restrict__ grad_sigma_regul, int max_d) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= G.M) return;
+  const float tf = tindex[(size_t)n * G.M + c];
+  if (tf < 0.f) return;
+  const int t = (int)tf;
+  if (G.T != 1 && t >= G.T) return;
+  const int ts = (G.T == 1) ? 0 : t;
+  const size_t vol = (size_t)G.Z * G.Y * G.X;
+  const size_t foff = ((size_t)n * G.T + ts) * vol;
+  const size_t ray = (size_t)n * G.M + c;
+  const float* e = em + ray * max_d;
+  const float* id = indices + ray * max_d * 3;
+  for (int i = lane; i < max_d; i += 32) {
+    const float v = e[i];
+    const bool reg = indicator && indicator[ray * max_d + i] >= 0.f;
+    if (v == 0.f && !reg) continue;
+    const int z = (int)id[i * 3], y = (int)id[i * 3 + 1], x = (int)id[i * 3 + 2];
+    if (z < 0 || z >= G.Z || y < 0 || y >= G.Y || x < 0 || x >= G.X) continue;
+    const size_t vo = foff + ((size_t)z * G.Y + y) * G.X + x;
+    if (v != 0.f) red_add_f32(grad_sigma + vo, v);
+    if (reg) {
+      const float gr = grad_ray_pred[ray * max_d + i];
+      if (gr != 0.f) red_add_f32(grad_sigma_regul + vo, gr);
+    }
+  }
+}
+
+int check_grid(Grid& G, int N, int M, int T, int To, int Z, int Y, int X, const char* who) {
+  VIDAR_REQUIRE(N > 0 && M >= 0 && T > 0 && To > 0 && Z > 0 && Y > 0 && X > 0,
+                "%s: bad sizes N=%d M=%d T=%d To=%d grid=%dx%dx%d", who, N, M, T, To, Z, Y, X);
+  VIDAR_REQUIRE(N <= 65535, "%s: batch %d exceeds gridDim.y", who, N);
+  G = Grid{N, M, T, To, Z, Y, X};
+  return VIDAR_OK;
+}
+
+inline dim3 ray_grid(const Grid& G, int per_block) {
+  return dim3((unsigned)((G.M + per_block - 1) / per_block), (unsigned)G.N);
+}
+
+}  // namespace
+}  // namespace vidar
+
+using namespace vidar;
+
+extern "C" int vidar_dvr_init(const float* points, const float* tindex, float* occupancy, int N,
+                              int M, int T, int Z, int Y, int X, void* stream) {
+  Grid G;
+  int rc = check_grid(G, N, M, T, T, Z, Y, X, "dvr.init");
+  if (rc) return rc;
+  VIDAR_REQUIRE(points && tindex && occupancy, "dvr.init: null pointer argument");
+  if (M == 0) return VIDAR_OK;
+  init_kernel<<<ray_grid(G, 256), 256, 0, (cudaStream_t)stream>>>(G, points, tindex, occupancy);
+  return check_launch("dvr.init");
+}
+
+extern "C" int vidar_dvr_render_forward(const float* sigma, const float* origin,
+                                        const float* points, const float* tindex,
+                                        float* pred_dist, float* gt_dist, int N, int M, int T,
+                                        int To, int Z, int Y, int X, int train_phase,
+                                        void* stream) {
+  Grid G;
+  int rc = check_grid(G, N, M, T, To, Z, Y, X, "dvr.render_forward");
+  if (rc) return rc;
+  VIDAR_REQUIRE(sigma && origin && points && tindex && pred_dist && gt_dist,
+                "dvr.render_forward: null pointer argument");
+  VIDAR_REQUIRE(train_phase == 0 || train_phase == 1, "UNKNOWN PHASE NAME: %d", train_phase);
+  if (M == 0) return VIDAR_OK;
+  forward_kernel<V_DVR_FWD><<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
+      G, sigma, origin, points, tindex, pred_dist, gt_dist, train_phase);
+  return check_launch("dvr.render_forward");
+}
+
+extern "C" int vidar_dvr_render(const float* sigma, const float* origin, const float* points,
+                                const float* tindex, float* pred_dist, float* gt_dist,
+                                float* grad_sigma, int N, int M, int T, int To, int Z, int Y,
+                                int X, int loss_type, void* stream) {
+  Grid G;
+  int rc = check_grid(G, N, M, T, To, Z, Y, X, "dvr.render");
+  if (rc) return rc;
+  VIDAR_REQUIRE(sigma && origin && points && tindex && pred_dist && gt_dist && grad_sigma,
+                "dvr.render: null pointer argument");
+  VIDAR_REQUIRE(loss_type >= 0 && loss_type <= 2, "UNKNOWN LOSS TYPE: %d", loss_type);
+  if (M == 0) return VIDAR_OK;
+  render_grad_kernel<<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
+      G, sigma, origin, points, tindex, pred_dist, gt_dist, grad_sigma, loss_type);
+  return check_launch("dvr.render");
+}
+
+extern "C" int vidar_dvxlr_forward(const float* sigma, const float* origin, const float* points,
+                                   const float* tindex, float* pred_dist, float* gt_dist, int N,
+                                   int M, int T, int To, int Z, int Y, int X, void* stream) {
+  Grid G;
+  int rc = check_grid(G, N, M, T, To, Z, Y, X, "dvxlr.forward");
+  if (rc) return rc;
+  VIDAR_REQUIRE(sigma && origin && points && tindex && pred_dist && gt_dist,
+                "dvxlr.forward: null pointer argument");
+  if (M == 0) return VIDAR_OK;
+  forward_kernel<V_DVXLR><<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
+      G, sigma, origin, points, tindex, pred_dist, gt_dist, 1);
+  return check_launch("dvxlr.forward");
+}
+
+extern "C" int vidar_dvxlr_render(const float* sigma, const float* origin, const float* points,
+                                  const float* tindex, const float* sigma_regul,
+                                  float* pred_dist, float* gt_dist, float* dd_dsigma,
+                                  float* indices, float* ray_pred, float* indicator, int N, int M,
+                                  int T, int To, int Z, int Y, int X, int max_d, void* stream) {
+  Grid G;
+  int rc = check_grid(G, N, M, T, To, Z, Y, X, "dvxlr.render");
+  if (rc) return rc;
+  VIDAR_REQUIRE(sigma && origin && points && tindex && pred_dist && gt_dist,
+                "dvxlr.render: null pointer argument");
+  VIDAR_REQUIRE((dd_dsigma == nullptr) == (indices == nullptr),
+                "dvxlr.render: dd_dsigma and indices go together");
+  VIDAR_REQUIRE(max_d > 0, "dvxlr.render: max_d must be positive");
+  const bool v2 = sigma_regul || ray_pred || indicator;
+  VIDAR_REQUIRE(!v2 || (sigma_regul && ray_pred && indicator),
+                "dvxlr.render_v2: sigma_regul, ray_pred and indicator must all be given");
+  if (M == 0) return VIDAR_OK;
+  dvxlr_list_kernel<<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
+      G, sigma, origin, points, tindex, sigma_regul, pred_dist, gt_dist, dd_dsigma, indices,
+      ray_pred, indicator, max_d);
+  return check_launch("dvxlr.render");
+}
+
+extern "C" int vidar_dvxlr_get_grad_sigma(const float* elementwise_mult, const float* indices,
+                                          const float* tindex, const float* indicator,
+                                          const float* grad_ray_pred, float* grad_sigma,
+                                          float* grad_sigma_regul, int N, int M, int T, int Z,
+                                          int Y, int X, int max_d, void* stream) {
+  Grid G;
+  int rc = check_grid(G, N, M, T, T, Z, Y, X, "dvxlr.get_grad_sigma");
+  if (rc) return rc;
+  VIDAR_REQUIRE(elementwise_mult && indices && tindex && grad_sigma,
+                "dvxlr.get_grad_sigma: null pointer argument");
+  const bool v2 = indicator || grad_ray_pred || grad_sigma_regul;
+  VIDAR_REQUIRE(!v2 || (indicator && grad_ray_pred && grad_sigma_regul),
+                "dvxlr.get_grad_sigma_v2: indicator, grad_ray_pred and grad_sigma_regul must all be given");
+  VIDAR_REQUIRE(max_d > 0, "dvxlr.get_grad_sigma: max_d must be positive");
+  if (M == 0) return VIDAR_OK;
+  list_scatter_kernel<<<ray_grid(G, 8), 256, 0, (cudaStream_t)stream>>>(
+      G, elementwise_mult, indices, tindex, indicator, grad_ray_pred, grad_sigma, grad_sigma_regul,
+      max_d);
+  return check_launch("dvxlr.get_grad_sigma");
+}
+
+extern "C" int vidar_dvxlr_backward_fused(const float* sigma, const float* origin,
+                                          const float* points, const float* tindex,
+                                          const float* grad_pred, const float* grad_ray_pred,
+                                          float* grad_sigma, float* grad_sigma_regul, int N,
+                                          int M, int T, int To, int Z, int Y, int X, int max_d,
+                                          void* stream) {
+  Grid G;
+  int rc = check_grid(G, N, M, T, To, Z, Y, X, "dvxlr.backward_fused");
+  if (rc) return rc;
+  VIDAR_REQUIRE(sigma && origin && points && tindex && grad_pred && grad_sigma,
+                "dvxlr.backward_fused: null pointer argument");
+  VIDAR_REQUIRE((grad_ray_pred == nullptr) == (grad_sigma_regul == nullptr),
+                "dvxlr.backward_fused: grad_ray_pred and grad_sigma_regul go together");
+  VIDAR_REQUIRE(max_d > 0, "dvxlr.backward_fused: max_d must be positive");
+  if (M == 0) return VIDAR_OK;
+  dvxlr_fused_bwd_kernel<<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
+      G, sigma, origin, points, tindex, grad_pred, grad_ray_pred, grad_sigma, grad_sigma_regul,
+      max_d);
+  return check_launch("dvxlr.backward_fused");
+}

@@ -1,0 +1,485 @@
+// Multi-scale deformable attention, forward + backward, for B200 (sm_100a).
+//
+// Replaces mmcv-full 1.4.0 `_ext.ms_deform_attn_{forward,backward}` as called from
+// projects/mmdet3d_plugin/bevformer/modules/multi_scale_deformable_attn_function.py:118-124,150-160.
+// Semantics: pixel = loc * (W,H) - 0.5, bilinear with per-corner zero
+// padding, a sample contributes only if -1 < pixel < size; out = sum_{l,p} w * bilerp.
+//
+// Mapping.  The op is a sparse gather: per (b, q, h) it reads L*P samples x 4 corners x C
+// floats (one 128-byte line per corner for C = 32).  One warp owns 32 samples at a time:
+//   * lane j decodes sample j once (coordinates, corner offsets, validity) -- the
+//     reference re-derives this once per *channel* thread (32x redundant);
+//   * the warp is then split into NG = 32/CV groups of CV lanes, a lane holding 4
+//     consecutive channels (float4): every corner fetch is a 16-byte vector load and a
+//     group of CV lanes covers one head vector, so a warp-level load instruction
+//     touches NG lines instead of 1 (4x fewer LSU instructions than lane = channel);
+//   * sample parameters travel from the decoding lane to its group by warp shuffle;
+//   * backward reduces grad_loc / grad_attn over channels with a 4-value transposed
+//     shuffle reduction (no shared memory, no __syncthreads -- the reference does a
+//     smem write + 2 barriers + a serial 32-way sum per sample), and scatters
+//     grad_value with 16-byte vector reductions (red.global.add.v4.f32).
+// Work order: for L*P >= 32 a block is 8 consecutive queries of one (b, h) and
+// neighbouring blocks are the other heads of the same queries, so the lines a block
+// touches are neighbours in the image (L1/L2 locality).
+#include "common.cuh"
+
+namespace vidar {
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+struct MsdaParams {
+  const float* value;
+  const int64_t* shapes;
+  const int64_t* lsi;
+  const float* loc;
+  const float* attn;
+  int B, K, H, C, L, Q, P, LP;
+  int ipw;            // items (b,q,h) per warp
+  long long items;    // B*Q*H
+};
+
+// Decode one sample: pixel coordinates -> clamped base pixel, corner mask, fractions.
+// meta = mask(4b) | dx << 4 | dyW << 5 ; mask == 0 <=> sample contributes nothing.
+__device__ __forceinline__ void decode_sample(float lx, float ly, int Hl, int Wl, int start,
+                                              int& base, int& meta, float& lh, float& lw) {
+  // mmcv: h_im = loc_h * spatial_h - 0.5 (no fused multiply-add there either)
+  const float h_im = __fsub_rn(__fmul_rn(ly, (float)Hl), 0.5f);
+  const float w_im = __fsub_rn(__fmul_rn(lx, (float)Wl), 0.5f);
+  base = 0;
+  meta = 0;
+  lh = 0.f;
+  lw = 0.f;
+  if (h_im > -1.f && w_im > -1.f && h_im < (float)Hl && w_im < (float)Wl) {
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    const int h_low = (int)hf, w_low = (int)wf;
+    lh = h_im - hf;
+    lw = w_im - wf;
+    const bool h0 = h_low >= 0, w0 = w_low >= 0;
+    const bool h1 = h_low + 1 <= Hl - 1, w1 = w_low + 1 <= Wl - 1;
+    const int mask = (int)(h0 && w0) | ((int)(h0 && w1) << 1) | ((int)(h1 && w0) << 2) |
+                     ((int)(h1 && w1) << 3);
+    const int hl = max(h_low, 0), wl = max(w_low, 0);
+    const int hh = min(h_low + 1, Hl - 1), wh = min(w_low + 1, Wl - 1);
+    base = start + hl * Wl + wl;
+    meta = mask | ((wh - wl) << 4) | (((hh - hl) * Wl) << 5);
+  }
+}
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_fma(float4& a, float s, const float4& v) {
+  a.x = fmaf(s, v.x, a.x);
+  a.y = fmaf(s, v.y, a.y);
+  a.z = fmaf(s, v.z, a.z);
+  a.w = fmaf(s, v.w, a.w);
+}
+__device__ __forceinline__ float f4_dot(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ float4 f4_scale(float s, const float4& v) {
+  return make_float4(s * v.x, s * v.y, s * v.z, s * v.w);
+}
+
+// Which (b,q,h) items does this warp own?  Returns false if none.
+//  ipw == 1 : block = 8 consecutive queries of one (b,h); blocks ordered (b, qtile, h).
+//  ipw  > 1 : ipw consecutive items in memory order (heads of the same query first).
+__device__ __forceinline__ bool warp_items(const MsdaParams& p, long long& item0) {
+  const int warp = threadIdx.x >> 5;
+  if (p.ipw == 1) {
+    const long long blk = blockIdx.x;
+    const int nqt = (p.Q + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int h = (int)(blk % p.H);
+    const int qt = (int)((blk / p.H) % nqt);
+    const int b = (int)(blk / ((long long)p.H * nqt));
+    const int q = qt * kWarpsPerBlock + warp;
+    if (q >= p.Q) return false;
+    item0 = ((long long)b * p.Q + q) * p.H + h;
+    return true;
+  }
+  item0 = ((long long)blockIdx.x * kWarpsPerBlock + warp) * p.ipw;
+  return item0 < p.items;
+}
+
+template <int CV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
+  constexpr int NG = 32 / CV;       // sample groups per warp
+  constexpr int ITERS = 32 / NG;    // == CV
+  const int lane = threadIdx.x & 31;
+  const int g = lane / CV;          // group = which sample of the current NG
+  const int cl = lane % CV;         // which float4 of the head vector
+  long long item0;
+  if (!warp_items(p, item0)) return;
+
+  const int span = p.ipw * p.LP;                       // samples owned by this warp
+  const int nchunks = (span + 31) >> 5;
+  const size_t pix_stride = (size_t)p.H * p.C;         // floats between pixels
+  const float* loc0 = p.loc + (size_t)item0 * p.LP * 2;
+  const float* att0 = p.attn + (size_t)item0 * p.LP;
+  const int items_per_iter_den = p.LP;                 // sample -> item_local = s / LP
+
+  float4 acc = f4_zero();
+  int cur_item = 0;  // item_local the accumulator belongs to (warp-uniform)
+
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    // ---- lane j decodes sample j of the chunk
+    const int s = chunk * 32 + lane;
+    int base = 0, meta = 0;
+    float lh = 0.f, lw = 0.f, aw = 0.f;
+    if (s < span && item0 + s / items_per_iter_den < p.items) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc0) + s);
+      aw = __ldg(att0 + s);
+      const int l = (s % p.LP) / p.P;
+      const int Hl = (int)__ldg(p.shapes + 2 * l), Wl = (int)__ldg(p.shapes + 2 * l + 1);
+      decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw);
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int slot0 = chunk * 32 + it * NG;  // first sample of this iteration (uniform)
+      if (slot0 >= span) break;
+      const int item_local = slot0 / p.LP;
+      if (item_local != cur_item) {
+        // flush finished item: sum the NG partial accumulators, group 0 stores
+#pragma unroll
+        for (int off = CV; off < 32; off <<= 1) {
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+          acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+          acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+        }
+        const long long item = item0 + cur_item;
+        if (g == 0 && item < p.items)
+          *reinterpret_cast<float4*>(out + (size_t)item * p.C + cl * 4) = acc;
+        acc = f4_zero();
+        cur_item = item_local;
+      }
+      const int src = it * NG + g;
+      const int sbase = __shfl_sync(0xffffffffu, base, src);
+      const int smeta = __shfl_sync(0xffffffffu, meta, src);
+      const float slh = __shfl_sync(0xffffffffu, lh, src);
+      const float slw = __shfl_sync(0xffffffffu, lw, src);
+      const float saw = __shfl_sync(0xffffffffu, aw, src);
+      const int mask = smeta & 15;
+      if (mask) {
+        const long long item = item0 + item_local;
+        const int h = (int)(item % p.H);
+        const int b = (int)(item / ((long long)p.Q * p.H));
+        const float* vb = p.value + ((size_t)b * p.K * p.H + h) * p.C + cl * 4;
+        const size_t dx = (size_t)((smeta >> 4) & 1) * pix_stride;
+        const size_t dy = (size_t)(smeta >> 5) * pix_stride;
+        const float* p1 = vb + (size_t)sbase * pix_stride;
+        float4 v1 = f4_zero(), v2 = f4_zero(), v3 = f4_zero(), v4 = f4_zero();
+        if (mask & 1) v1 = ldg4(p1);
+        if (mask & 2) v2 = ldg4(p1 + dx);
+        if (mask & 4) v3 = ldg4(p1 + dy);
+        if (mask & 8) v4 = ldg4(p1 + dy + dx);
+        const float hh = 1.f - slh, hw = 1.f - slw;
+        f4_fma(acc, saw * (hh * hw), v1);
+        f4_fma(acc, saw * (hh * slw), v2);
+        f4_fma(acc, saw * (slh * hw), v3);
+        f4_fma(acc, saw * (slh * slw), v4);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = CV; off < 32; off <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+  }
+  const long long item = item0 + cur_item;
+  if (g == 0 && item < p.items)
+    *reinterpret_cast<float4*>(out + (size_t)item * p.C + cl * 4) = acc;
+}
+
+template <int CV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
+                     float* __restrict__ grad_value, float* __restrict__ grad_loc,
+                     float* __restrict__ grad_attn) {
+  constexpr int NG = 32 / CV;
+  constexpr int ITERS = 32 / NG;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / CV;
+  const int cl = lane % CV;
+  long long item0;
+  if (!warp_items(p, item0)) return;
+
+  const int span = p.ipw * p.LP;
+  const int nchunks = (span + 31) >> 5;
+  const size_t pix_stride = (size_t)p.H * p.C;
+  const float* loc0 = p.loc + (size_t)item0 * p.LP * 2;
+  const float* att0 = p.attn + (size_t)item0 * p.LP;
+  float* gloc0 = grad_loc + (size_t)item0 * p.LP * 2;
+  float* gatt0 = grad_attn + (size_t)item0 * p.LP;
+
+  int cur_item = -1;
+  float4 go = f4_zero();
+
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    const int s = chunk * 32 + lane;
+    int base = 0, meta = 0;
+    float lh = 0.f, lw = 0.f, aw = 0.f, fH = 0.f, fW = 0.f;
+    if (s < span && item0 + s / p.LP < p.items) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc0) + s);
+      aw = __ldg(att0 + s);
+      const int l = (s % p.LP) / p.P;
+      const int Hl = (int)__ldg(p.shapes + 2 * l), Wl = (int)__ldg(p.shapes + 2 * l + 1);
+      decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw);
+      fH = (float)Hl;
+      fW = (float)Wl;
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int slot0 = chunk * 32 + it * NG;
+      if (slot0 >= span) break;
+      const int item_local = slot0 / p.LP;
+      const long long item = item0 + item_local;
+      if (item >= p.items) break;
+      const int h = (int)(item % p.H);
+      const int b = (int)(item / ((long long)p.Q * p.H));
+      if (item_local != cur_item) {
+        cur_item = item_local;
+        go = ldg4(grad_out + (size_t)item * p.C + cl * 4);
+      }
+      const int src = it * NG + g;
+      const int sbase = __shfl_sync(0xffffffffu, base, src);
+      const int smeta = __shfl_sync(0xffffffffu, meta, src);
+      const float slh = __shfl_sync(0xffffffffu, lh, src);
+      const float slw = __shfl_sync(0xffffffffu, lw, src);
+      const float saw = __shfl_sync(0xffffffffu, aw, src);
+      const float sH = __shfl_sync(0xffffffffu, fH, src);
+      const float sW = __shfl_sync(0xffffffffu, fW, src);
+      const int mask = smeta & 15;
+      float ga = 0.f, gx = 0.f, gy = 0.f;
+      if (mask) {
+        const size_t off0 = ((size_t)b * p.K * p.H + h) * p.C + cl * 4 + (size_t)sbase * pix_stride;
+        const size_t dx = (size_t)((smeta >> 4) & 1) * pix_stride;
+        const size_t dy = (size_t)(smeta >> 5) * pix_stride;
+        float4 v1 = f4_zero(), v2 = f4_zero(), v3 = f4_zero(), v4 = f4_zero();
+        if (mask & 1) v1 = ldg4(p.value + off0);
+        if (mask & 2) v2 = ldg4(p.value + off0 + dx);
+        if (mask & 4) v3 = ldg4(p.value + off0 + dy);
+        if (mask & 8) v4 = ldg4(p.value + off0 + dy + dx);
+        const float hh = 1.f - slh, hw = 1.f - slw;
+        const float w1 = hh * hw, w2 = hh * slw, w3 = slh * hw, w4 = slh * slw;
+        // grad_value: top_grad * attn * corner weight, 16-byte vector reductions
+        if (mask & 1) red_add_v4(grad_value + off0, f4_scale(saw * w1, go));
+        if (mask & 2) red_add_v4(grad_value + off0 + dx, f4_scale(saw * w2, go));
+        if (mask & 4) red_add_v4(grad_value + off0 + dy, f4_scale(saw * w3, go));
+        if (mask & 8) red_add_v4(grad_value + off0 + dy + dx, f4_scale(saw * w4, go));
+        const float d1 = f4_dot(go, v1), d2 = f4_dot(go, v2);
+        const float d3 = f4_dot(go, v3), d4 = f4_dot(go, v4);
+        ga = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;
+        gx = sW * saw * (hh * (d2 - d1) + slh * (d4 - d3));
+        gy = sH * saw * (hw * (d3 - d1) + slw * (d4 - d2));
+      }
+      // ---- transposed reduction of (ga, gx, gy, 0) over the CV lanes of the group
+      {
+        const bool up1 = (cl & (CV / 2)) != 0;
+        const float s0 = up1 ? ga : gy;
+        const float s1 = up1 ? gx : 0.f;
+        const float r0 = __shfl_xor_sync(0xffffffffu, s0, CV / 2);
+        const float r1 = __shfl_xor_sync(0xffffffffu, s1, CV / 2);
+        const float k0 = (up1 ? gy : ga) + r0;    // lower half: ga   upper half: gy
+        const float k1 = (up1 ? 0.f : gx) + r1;   // lower half: gx   upper half: 0
+        const bool up2 = (cl & (CV / 4)) != 0;
+        const float sb = up2 ? k0 : k1;
+        const float rb = __shfl_xor_sync(0xffffffffu, sb, CV / 4);
+        float k = (up2 ? k1 : k0) + rb;  // (0,0): ga  (0,1): gx  (1,0): gy  (1,1): 0
+#pragma unroll
+        for (int off = CV / 8; off >= 1; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
+        const int sidx = chunk * 32 + src;  // sample index inside the warp span
+        if (sidx < span) {
+          if (cl == 0) gatt0[sidx] = k;
+          else if (cl == CV / 4) gloc0[2 * sidx] = k;
+          else if (cl == CV / 2) gloc0[2 * sidx + 1] = k;
+        }
+      }
+    }
+  }
+}
+
+// ---- generic fallback (any C): one thread per (item, channel); scalar atomics.
+__global__ void msda_forward_generic_kernel(const MsdaParams p, float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.items * p.C) return;
+  const int c = (int)(idx % p.C);
+  const long long item = idx / p.C;
+  const int h = (int)(item % p.H);
+  const int b = (int)(item / ((long long)p.Q * p.H));
+  const size_t pix_stride = (size_t)p.H * p.C;
+  const float* vb = p.value + ((size_t)b * p.K * p.H + h) * p.C + c;
+  float acc = 0.f;
+  for (int s = 0; s < p.LP; ++s) {
+    const int l = s / p.P;
+    const int Hl = (int)p.shapes[2 * l], Wl = (int)p.shapes[2 * l + 1];
+    int base, meta;
+    float lh, lw;
+    decode_sample(p.loc[((size_t)item * p.LP + s) * 2], p.loc[((size_t)item * p.LP + s) * 2 + 1],
+                  Hl, Wl, (int)p.lsi[l], base, meta, lh, lw);
+    const int mask = meta & 15;
+    if (!mask) continue;
+    const float aw = p.attn[(size_t)item * p.LP + s];
+    const size_t dx = (size_t)((meta >> 4) & 1) * pix_stride, dy = (size_t)(meta >> 5) * pix_stride;
+    const float* p1 = vb + (size_t)base * pix_stride;
+    const float v1 = (mask & 1) ? p1[0] : 0.f, v2 = (mask & 2) ? p1[dx] : 0.f;
+    const float v3 = (mask & 4) ? p1[dy] : 0.f, v4 = (mask & 8) ? p1[dy + dx] : 0.f;
+    const float hh = 1.f - lh, hw = 1.f - lw;
+    acc += aw * (hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4);
+  }
+  out[idx] = acc;
+}
+
+__global__ void msda_backward_generic_kernel(const MsdaParams p, const float* __restrict__ grad_out,
+                                             float* __restrict__ grad_value,
+                                             float* __restrict__ grad_loc,
+                                             float* __restrict__ grad_attn) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.items * p.C) return;
+  const int c = (int)(idx % p.C);
+  const long long item = idx / p.C;
+  const int h = (int)(item % p.H);
+  const int b = (int)(item / ((long long)p.Q * p.H));
+  const size_t pix_stride = (size_t)p.H * p.C;
+  const size_t voff = ((size_t)b * p.K * p.H + h) * p.C + c;
+  const float go = grad_out[idx];
+  for (int s = 0; s < p.LP; ++s) {
+    const int l = s / p.P;
+    const int Hl = (int)p.shapes[2 * l], Wl = (int)p.shapes[2 * l + 1];
+    int base, meta;
+    float lh, lw;
+    const size_t si = (size_t)item * p.LP + s;
+    decode_sample(p.loc[si * 2], p.loc[si * 2 + 1], Hl, Wl, (int)p.lsi[l], base, meta, lh, lw);
+    const int mask = meta & 15;
+    if (!mask) continue;
+    const float aw = p.attn[si];
+    const size_t dx = (size_t)((meta >> 4) & 1) * pix_stride, dy = (size_t)(meta >> 5) * pix_stride;
+    const size_t o1 = voff + (size_t)base * pix_stride;
+    const float v1 = (mask & 1) ? p.value[o1] : 0.f, v2 = (mask & 2) ? p.value[o1 + dx] : 0.f;
+    const float v3 = (mask & 4) ? p.value[o1 + dy] : 0.f, v4 = (mask & 8) ? p.value[o1 + dy + dx] : 0.f;
+    const float hh = 1.f - lh, hw = 1.f - lw;
+    const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+    const float top = go * aw;
+    if (mask & 1) red_add_f32(grad_value + o1, w1 * top);
+    if (mask & 2) red_add_f32(grad_value + o1 + dx, w2 * top);
+    if (mask & 4) red_add_f32(grad_value + o1 + dy, w3 * top);
+    if (mask & 8) red_add_f32(grad_value + o1 + dy + dx, w4 * top);
+    red_add_f32(grad_attn + si, go * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4));
+    red_add_f32(grad_loc + si * 2, (float)Wl * top * (hh * (v2 - v1) + lh * (v4 - v3)));
+    red_add_f32(grad_loc + si * 2 + 1, (float)Hl * top * (hw * (v3 - v1) + lw * (v4 - v2)));
+  }
+}
+
+int fill_params(MsdaParams& p, const float* value, const int64_t* shapes, const int64_t* lsi,
+                const float* loc, const float* attn, int B, int K, int H, int C, int L, int Q,
+                int P, int im2col_step, const char* who) {
+  VIDAR_REQUIRE(value && shapes && lsi && loc && attn, "%s: null pointer argument", who);
+  VIDAR_REQUIRE(B > 0 && K > 0 && H > 0 && C > 0 && L > 0 && Q > 0 && P > 0,
+                "%s: all of B,K,H,C,L,Q,P must be positive (got %d,%d,%d,%d,%d,%d,%d)", who, B, K,
+                H, C, L, Q, P);
+  VIDAR_REQUIRE(im2col_step > 0, "%s: im2col_step must be positive", who);
+  const int step = im2col_step < B ? im2col_step : B;
+  // mmcv: AT_ASSERTM(batch % im2col_step_ == 0, "batch(%d) must divide im2col_step(%d)")
+  VIDAR_REQUIRE(B % step == 0, "%s: batch(%d) must divide im2col_step(%d)", who, B, step);
+  p.value = value;
+  p.shapes = shapes;
+  p.lsi = lsi;
+  p.loc = loc;
+  p.attn = attn;
+  p.B = B; p.K = K; p.H = H; p.C = C; p.L = L; p.Q = Q; p.P = P;
+  p.LP = L * P;
+  p.items = (long long)B * Q * H;
+  p.ipw = 1;
+  return VIDAR_OK;
+}
+
+inline bool vec_ok(int C) { return C == 16 || C == 32 || C == 64; }
+
+// items per warp for the vector kernels: pack several (b,q,h) into one 32-sample chunk
+// when L*P is small (temporal self-attention: L*P = 4).
+inline int pick_ipw(int LP, int CV) {
+  const int NG = 32 / CV;
+  if (LP < 32 && 32 % LP == 0 && LP % NG == 0) return 32 / LP;
+  return 1;
+}
+
+inline long long num_blocks(const MsdaParams& p) {
+  if (p.ipw == 1) {
+    const long long nqt = (p.Q + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    return (long long)p.B * nqt * p.H;
+  }
+  const long long warps = (p.items + p.ipw - 1) / p.ipw;
+  return (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+}
+
+}  // namespace
+}  // namespace vidar
+
+using namespace vidar;
+
+extern "C" int vidar_msda_forward(const float* value, const int64_t* spatial_shapes,
+                                  const int64_t* level_start, const float* sampling_loc,
+                                  const float* attn_weight, float* out, int B, int K, int H, int C,
+                                  int L, int Q, int P, int im2col_step, void* stream) {
+  MsdaParams p;
+  int rc = fill_params(p, value, spatial_shapes, level_start, sampling_loc, attn_weight, B, K, H,
+                       C, L, Q, P, im2col_step, "ms_deform_attn_forward");
+  if (rc) return rc;
+  VIDAR_REQUIRE(out, "ms_deform_attn_forward: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec_ok(C)) {
+    const int CV = C / 4;
+    p.ipw = pick_ipw(p.LP, CV);
+    const long long nb = num_blocks(p);
+    VIDAR_REQUIRE(nb < 2147483647LL, "ms_deform_attn_forward: problem too large");
+    const dim3 grid((unsigned)nb), block(kWarpsPerBlock * 32);
+    if (CV == 8) msda_forward_kernel<8><<<grid, block, 0, st>>>(p, out);
+    else if (CV == 4) msda_forward_kernel<4><<<grid, block, 0, st>>>(p, out);
+    else msda_forward_kernel<16><<<grid, block, 0, st>>>(p, out);
+  } else {
+    const long long n = p.items * C;
+    const long long nb = (n + 255) / 256;
+    VIDAR_REQUIRE(nb < 2147483647LL, "ms_deform_attn_forward: problem too large");
+    msda_forward_generic_kernel<<<(unsigned)nb, 256, 0, st>>>(p, out);
+  }
+  return check_launch("ms_deform_attn_forward");
+}
+
+extern "C" int vidar_msda_backward(const float* value, const int64_t* spatial_shapes,
+                                   const int64_t* level_start, const float* sampling_loc,
+                                   const float* attn_weight, const float* grad_out,
+                                   float* grad_value, float* grad_sampling_loc,
+                                   float* grad_attn_weight, int B, int K, int H, int C, int L,
+                                   int Q, int P, int im2col_step, void* stream) {
+  MsdaParams p;
+  int rc = fill_params(p, value, spatial_shapes, level_start, sampling_loc, attn_weight, B, K, H,
+                       C, L, Q, P, im2col_step, "ms_deform_attn_backward");
+  if (rc) return rc;
+  VIDAR_REQUIRE(grad_out && grad_value && grad_sampling_loc && grad_attn_weight,
+                "ms_deform_attn_backward: null gradient pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec_ok(C)) {
+    const int CV = C / 4;
+    p.ipw = pick_ipw(p.LP, CV);
+    const long long nb = num_blocks(p);
+    VIDAR_REQUIRE(nb < 2147483647LL, "ms_deform_attn_backward: problem too large");
+    const dim3 grid((unsigned)nb), block(kWarpsPerBlock * 32);
+    if (CV == 8)
+      msda_backward_kernel<8><<<grid, block, 0, st>>>(p, grad_out, grad_value, grad_sampling_loc, grad_attn_weight);
+    else if (CV == 4)
+      msda_backward_kernel<4><<<grid, block, 0, st>>>(p, grad_out, grad_value, grad_sampling_loc, grad_attn_weight);
+    else
+      msda_backward_kernel<16><<<grid, block, 0, st>>>(p, grad_out, grad_value, grad_sampling_loc, grad_attn_weight);
+  } else {
+    cudaError_t e = cudaMemsetAsync(grad_sampling_loc, 0, sizeof(float) * 2 * (size_t)p.items * p.LP, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(grad_attn_weight, 0, sizeof(float) * (size_t)p.items * p.LP, st);
+    if (e != cudaSuccess) return set_error(VIDAR_E_CUDA, "ms_deform_attn_backward: memset: %s", cudaGetErrorString(e));
+    const long long n = p.items * C;
+    const long long nb = (n + 255) / 256;
+    VIDAR_REQUIRE(nb < 2147483647LL, "ms_deform_attn_backward: problem too large");
+    msda_backward_generic_kernel<<<(unsigned)nb, 256, 0, st>>>(p, grad_out, grad_value, grad_sampling_loc, grad_attn_weight);
+  }
+  return check_launch("ms_deform_attn_backward");
+}
