@@ -1,0 +1,60 @@
+"""Host logic of the attention modules against goldens produced by the REFERENCE classes
+(tools/make_golden_modules.py).  No GPU here: the one CUDA call inside the modules
+(`msda_apply`) is replaced by the CPU oracle, so what is tested is everything around it --
+rebatching, Z-anchor broadcast, softmax layout, queue averaging, scatter-add, count
+normalisation, projections, parameter names."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import msda_ref
+from tests import module_cases as mc
+from vidar_b200.modules import deform_attn
+from vidar_b200.registry import ATTENTION, build_attention
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "modules.npz")
+
+
+@pytest.fixture()
+def oracle_msda(monkeypatch):
+    def apply(value, shapes, lsi, loc, attn, im2col_step):
+        return msda_ref.msda_grid_sample(value, shapes, loc, attn)
+    monkeypatch.setattr(deform_attn, "msda_apply", apply)
+
+
+@pytest.mark.parametrize("kind,cfg,case,seed", [("sca", mc.SCA_CFG, mc.sca_case, 10),
+                                                ("tsa", mc.TSA_CFG, mc.tsa_case, 11),
+                                                ("pred", mc.PRED_CFG, mc.pred_case, 12)])
+def test_module_matches_reference_class(oracle_msda, kind, cfg, case, seed):
+    g = np.load(GOLD)
+    m = build_attention(cfg)
+    assert sorted(m.state_dict().keys()) == list(g[f"{kind}_params"])     # checkpoints load unchanged
+    m.load_state_dict(mc.seeded_state(m, seed))
+    m.eval()
+    out, gq, gkv = mc.run_module(m, kind, case())
+    np.testing.assert_allclose(out.numpy(), g[f"{kind}_out"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(gq.numpy(), g[f"{kind}_gq"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(gkv[:, ::6].numpy(), g[f"{kind}_gkv_s6"], rtol=1e-4, atol=2e-5)
+
+
+def test_registry_names_and_default_init():
+    for name in ("SpatialCrossAttention", "MSDeformableAttention3D", "TemporalSelfAttention",
+                 "PredictionMSDeformableAttention"):
+        assert name in ATTENTION
+    m = build_attention(dict(type="MSDeformableAttention3D", embed_dims=256, num_points=8, num_levels=4))
+    b = m.sampling_offsets.bias.view(8, 4, 8, 2)
+    assert torch.allclose(b[0, 0, :, 0], torch.arange(1.0, 9.0))           # head 0 looks along +x, radius i+1
+    assert float(m.sampling_offsets.weight.abs().sum()) == 0.0
+    assert m.output_proj is None
+    with pytest.raises(KeyError):
+        build_attention(dict(type="NoSuchAttention"))
+
+
+def test_modules_have_no_cpu_fallback():
+    m = build_attention(mc.TSA_CFG)
+    c = mc.tsa_case()
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        m(c["query"], None, c["value"], reference_points=c["reference_points"],
+          spatial_shapes=c["spatial_shapes"], level_start_index=c["level_start_index"])

@@ -1,0 +1,27 @@
+"""The attention modules end to end on the GPU (CUDA MSDA op inside) against goldens produced
+by the REFERENCE classes on CPU (tools/make_golden_modules.py).  1e-4 relative fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import module_cases as mc
+from vidar_b200.registry import build_attention
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "modules.npz")
+
+
+@pytest.mark.parametrize("kind,cfg,case,seed", [("sca", mc.SCA_CFG, mc.sca_case, 10),
+                                                ("tsa", mc.TSA_CFG, mc.tsa_case, 11),
+                                                ("pred", mc.PRED_CFG, mc.pred_case, 12)])
+def test_module_on_gpu_matches_reference_class(cuda, kind, cfg, case, seed):
+    g = np.load(GOLD)
+    m = build_attention(cfg)
+    m.load_state_dict(mc.seeded_state(m, seed))
+    m.eval().to(cuda)
+    out, gq, gkv = mc.run_module(m, kind, case(), device=cuda)
+    np.testing.assert_allclose(out.cpu().numpy(), g[f"{kind}_out"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(gq.cpu().numpy(), g[f"{kind}_gq"], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(gkv[:, ::6].cpu().numpy(), g[f"{kind}_gkv_s6"], rtol=1e-4, atol=5e-5)

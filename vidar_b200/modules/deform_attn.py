@@ -1,0 +1,347 @@
+"""Deformable-attention modules of the BEV encoder / future decoder, host side.
+
+Same registry names, constructor kwargs, parameter names (`sampling_offsets`,
+`attention_weights`, `value_proj`, `output_proj`), forward kwargs and numerics as the reference
+classes, so the reference's config dicts build them and released checkpoints load:
+
+  MSDeformableAttention3D          spatial_cross_attention.py:177-398
+  SpatialCrossAttention            spatial_cross_attention.py:30-174
+  TemporalSelfAttention            temporal_self_attention.py:25-271
+  PredictionMSDeformableAttention  vidar_decoder.py:289-516
+(paths under projects/mmdet3d_plugin/bevformer/modules/ of the reference).
+
+Every sampling step goes through `msda_apply` = MultiScaleDeformableAttnFunction_fp32.apply,
+the CUDA op in vidar_b200/csrc/msda.cu.  There is no PyTorch fallback branch (the
+reference falls back to `multi_scale_deformable_attn_pytorch` on CPU tensors,
+spatial_cross_attention.py:392-394): CPU tensors raise.
+"""
+import math
+import warnings
+
+import torch
+import torch.nn as nn
+
+from ..msda import MultiScaleDeformableAttnFunction_fp32
+from ..registry import ATTENTION, BaseModule, build_attention, constant_init, xavier_init
+
+msda_apply = MultiScaleDeformableAttnFunction_fp32.apply
+
+
+def _check_heads(embed_dims, num_heads):
+    if embed_dims % num_heads != 0:
+        raise ValueError(f"embed_dims must be divisible by num_heads, but got {embed_dims} and {num_heads}")
+    d = embed_dims // num_heads
+    if not (isinstance(d, int) and d > 0 and (d & (d - 1)) == 0):
+        warnings.warn("You'd better set embed_dims in MultiScaleDeformAttention to make the dimension of "
+                      "each attention head a power of 2 which is more efficient in our CUDA implementation.")
+
+
+def _ring_offsets(num_heads, num_groups, num_points):
+    """Initial bias of `sampling_offsets`: head h looks along direction 2*pi*h/num_heads
+    (normalised to the unit square), point i at radius i+1 -> flat [heads*groups*points*2]
+    (spatial_cross_attention.py:255-266, temporal_self_attention.py:108-119)."""
+    theta = torch.arange(num_heads, dtype=torch.float32) * (2.0 * math.pi / num_heads)
+    d = torch.stack([theta.cos(), theta.sin()], -1)
+    d = d / d.abs().max(-1, keepdim=True)[0]
+    radius = torch.arange(1, num_points + 1, dtype=torch.float32)
+    g = d.view(num_heads, 1, 1, 2) * radius.view(1, 1, num_points, 1)
+    return g.expand(num_heads, num_groups, num_points, 2).reshape(-1).clone()
+
+
+def _wh(spatial_shapes):
+    """[L,2] (h,w) -> (w,h) normaliser for pixel offsets."""
+    return torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
+
+
+@ATTENTION.register_module()
+class MSDeformableAttention3D(BaseModule):
+    """Deformable attention whose reference points are the projections of a BEV pillar's
+    Z-anchors into one camera (spatial_cross_attention.py:177-398).  No output projection and
+    no residual here -- SpatialCrossAttention owns both."""
+
+    def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=8, im2col_step=64,
+                 dropout=0.1, batch_first=True, norm_cfg=None, init_cfg=None):
+        super().__init__(init_cfg)
+        _check_heads(embed_dims, num_heads)
+        self.norm_cfg = norm_cfg
+        self.batch_first = batch_first
+        self.output_proj = None
+        self.fp16_enabled = False
+        self.im2col_step = im2col_step
+        self.embed_dims = embed_dims
+        self.num_levels = num_levels
+        self.num_heads = num_heads
+        self.num_points = num_points
+        self.sampling_offsets = nn.Linear(embed_dims, num_heads * num_levels * num_points * 2)
+        self.attention_weights = nn.Linear(embed_dims, num_heads * num_levels * num_points)
+        self.value_proj = nn.Linear(embed_dims, embed_dims)
+        self.init_weights()
+
+    def init_weights(self):
+        constant_init(self.sampling_offsets, 0.)
+        self.sampling_offsets.bias.data = _ring_offsets(self.num_heads, self.num_levels, self.num_points)
+        constant_init(self.attention_weights, val=0., bias=0.)
+        xavier_init(self.value_proj, distribution="uniform", bias=0.)
+        self._is_init = True
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None,
+                key_padding_mask=None, reference_points=None, spatial_shapes=None,
+                level_start_index=None, **kwargs):
+        if value is None:
+            value = query
+        if query_pos is not None:
+            query = query + query_pos
+        if not self.batch_first:
+            query, value = query.permute(1, 0, 2), value.permute(1, 0, 2)
+        bs, num_query, _ = query.shape
+        num_value = value.shape[1]
+        assert (spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum() == num_value
+        H, L, P = self.num_heads, self.num_levels, self.num_points
+
+        value = self.value_proj(value)
+        if key_padding_mask is not None:
+            value = value.masked_fill(key_padding_mask[..., None], 0.0)
+        value = value.view(bs, num_value, H, -1)
+        offsets = self.sampling_offsets(query).view(bs, num_query, H, L, P, 2)
+        weights = self.attention_weights(query).view(bs, num_query, H, L * P).softmax(-1)
+        weights = weights.view(bs, num_query, H, L, P)
+
+        if reference_points.shape[-1] != 2:
+            raise ValueError(f"Last dim of reference_points must be 2, but get {reference_points.shape[-1]} instead.")
+        # point p = j * D + z samples around Z-anchor z  (:356-371)
+        D = reference_points.shape[2]
+        assert P % D == 0
+        offsets = offsets / _wh(spatial_shapes)[None, None, None, :, None, :]
+        loc = offsets.view(bs, num_query, H, L, P // D, D, 2) + reference_points[:, :, None, None, None, :, :]
+        loc = loc.view(bs, num_query, H, L, P, 2)
+
+        output = msda_apply(value, spatial_shapes, level_start_index, loc, weights, self.im2col_step)
+        if not self.batch_first:
+            output = output.permute(1, 0, 2)
+        return output
+
+
+@ATTENTION.register_module()
+class SpatialCrossAttention(BaseModule):
+    """BEV query -> 6 camera feature pyramids (spatial_cross_attention.py:30-174): each camera
+    attends only with the BEV pillars it sees, results are averaged over the cameras that
+    see a pillar, projected, and added to the residual."""
+
+    def __init__(self, embed_dims=256, num_cams=6, pc_range=None, dropout=0.1, init_cfg=None,
+                 batch_first=False,
+                 deformable_attention=dict(type="MSDeformableAttention3D", embed_dims=256, num_levels=4),
+                 **kwargs):
+        super().__init__(init_cfg)
+        self.init_cfg = init_cfg
+        self.dropout = nn.Dropout(dropout)
+        self.pc_range = pc_range
+        self.fp16_enabled = False
+        self.deformable_attention = build_attention(deformable_attention)
+        self.embed_dims = embed_dims
+        self.num_cams = num_cams
+        self.output_proj = nn.Linear(embed_dims, embed_dims)
+        self.batch_first = batch_first
+        self.init_weight()
+
+    def init_weight(self):
+        xavier_init(self.output_proj, distribution="uniform", bias=0.)
+
+    def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
+                reference_points=None, spatial_shapes=None, reference_points_cam=None,
+                bev_mask=None, level_start_index=None, flag="encoder", **kwargs):
+        if key is None:
+            key = query
+        if value is None:
+            value = key
+        inp_residual = query if residual is None else residual
+        if query_pos is not None:
+            query = query + query_pos
+        bs, num_query, C = query.shape
+        cams, D = self.num_cams, reference_points_cam.size(3)
+
+        # visible-pillar lists per camera, taken from batch element 0 like the reference (:136-140).
+        # One batched sort instead of 6 nonzero() calls; ONE host sync (max_len).
+        hit = bev_mask[:, 0].sum(-1) > 0                                     # [cams, Q]
+        counts = hit.sum(-1)
+        max_len = int(counts.max())
+        order = torch.argsort((~hit).to(torch.uint8), dim=1, stable=True)    # visible first, ascending
+        idx = order[:, :max_len]                                             # [cams, max_len]
+        live = torch.arange(max_len, device=query.device)[None, :] < counts[:, None]
+
+        # rebatch (:143-152): padded rows are zeros
+        q_re = query[:, idx] * live[None, :, :, None].to(query.dtype)        # [bs, cams, max_len, C]
+        cam_ix = torch.arange(cams, device=query.device)[:, None]
+        r_re = reference_points_cam[cam_ix, :, idx]                          # [cams, max_len, bs, D, 2]
+        r_re = r_re.permute(2, 0, 1, 3, 4) * live[None, :, :, None, None].to(r_re.dtype)
+
+        l = key.shape[1]
+        key = key.permute(2, 0, 1, 3).reshape(bs * cams, l, self.embed_dims)
+        value = value.permute(2, 0, 1, 3).reshape(bs * cams, l, self.embed_dims)
+        out = self.deformable_attention(
+            query=q_re.reshape(bs * cams, max_len, self.embed_dims), key=key, value=value,
+            reference_points=r_re.reshape(bs * cams, max_len, D, 2), spatial_shapes=spatial_shapes,
+            level_start_index=level_start_index).view(bs, cams, max_len, self.embed_dims)
+
+        # scatter-add back (:164-166); padded rows carry zeros so their target index is irrelevant
+        out = out * live[None, :, :, None].to(out.dtype)
+        slots = torch.zeros_like(query)
+        slots.index_add_(1, idx.reshape(-1), out.reshape(bs, cams * max_len, self.embed_dims))
+
+        count = (bev_mask.sum(-1) > 0).permute(1, 2, 0).sum(-1)              # [bs, Q] cameras seeing it
+        slots = slots / torch.clamp(count, min=1.0)[..., None]
+        slots = self.output_proj(slots)
+        return self.dropout(slots) + inp_residual
+
+
+@ATTENTION.register_module()
+class TemporalSelfAttention(BaseModule):
+    """BEV self-attention over [previous BEV, current BEV] (temporal_self_attention.py:25-271):
+    offsets/weights are predicted from concat(prev, cur), each queue element is sampled
+    separately (batch = bs * num_bev_queue) and the two results are averaged."""
+
+    def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=4, num_bev_queue=2,
+                 im2col_step=64, dropout=0.1, batch_first=True, norm_cfg=None, init_cfg=None):
+        super().__init__(init_cfg)
+        _check_heads(embed_dims, num_heads)
+        self.norm_cfg = norm_cfg
+        self.dropout = nn.Dropout(dropout)
+        self.batch_first = batch_first
+        self.fp16_enabled = False
+        self.im2col_step = im2col_step
+        self.embed_dims = embed_dims
+        self.num_levels = num_levels
+        self.num_heads = num_heads
+        self.num_points = num_points
+        self.num_bev_queue = num_bev_queue
+        self.sampling_offsets = nn.Linear(embed_dims * num_bev_queue,
+                                          num_bev_queue * num_heads * num_levels * num_points * 2)
+        self.attention_weights = nn.Linear(embed_dims * num_bev_queue,
+                                           num_bev_queue * num_heads * num_levels * num_points)
+        self.value_proj = nn.Linear(embed_dims, embed_dims)
+        self.output_proj = nn.Linear(embed_dims, embed_dims)
+        self.init_weights()
+
+    def init_weights(self):
+        constant_init(self.sampling_offsets, 0.)
+        self.sampling_offsets.bias.data = _ring_offsets(
+            self.num_heads, self.num_levels * self.num_bev_queue, self.num_points)
+        constant_init(self.attention_weights, val=0., bias=0.)
+        xavier_init(self.value_proj, distribution="uniform", bias=0.)
+        xavier_init(self.output_proj, distribution="uniform", bias=0.)
+        self._is_init = True
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None,
+                key_padding_mask=None, reference_points=None, spatial_shapes=None,
+                level_start_index=None, flag="decoder", **kwargs):
+        if value is None:
+            assert self.batch_first
+            bs, len_bev, c = query.shape
+            value = torch.stack([query, query], 1).reshape(bs * 2, len_bev, c)
+        if identity is None:
+            identity = query
+        if query_pos is not None:
+            query = query + query_pos
+        if not self.batch_first:
+            query, value = query.permute(1, 0, 2), value.permute(1, 0, 2)
+        bs, num_query, embed_dims = query.shape
+        num_value = value.shape[1]
+        assert (spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum() == num_value
+        assert self.num_bev_queue == 2
+        H, L, P, Qn = self.num_heads, self.num_levels, self.num_points, self.num_bev_queue
+
+        query = torch.cat([value[:bs], query], -1)
+        value = self.value_proj(value)
+        if key_padding_mask is not None:
+            value = value.masked_fill(key_padding_mask[..., None], 0.0)
+        value = value.reshape(bs * Qn, num_value, H, -1)
+
+        offsets = self.sampling_offsets(query).view(bs, num_query, H, Qn, L, P, 2)
+        weights = self.attention_weights(query).view(bs, num_query, H, Qn, L * P).softmax(-1)
+        weights = weights.view(bs, num_query, H, Qn, L, P)
+        # queue axis next to batch: [bs*Qn, num_query, H, L, P(,2)]
+        weights = weights.permute(0, 3, 1, 2, 4, 5).reshape(bs * Qn, num_query, H, L, P).contiguous()
+        offsets = offsets.permute(0, 3, 1, 2, 4, 5, 6).reshape(bs * Qn, num_query, H, L, P, 2)
+
+        if reference_points.shape[-1] == 2:
+            loc = reference_points[:, :, None, :, None, :] + offsets / _wh(spatial_shapes)[None, None, None, :, None, :]
+        elif reference_points.shape[-1] == 4:
+            loc = (reference_points[:, :, None, :, None, :2]
+                   + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5)
+        else:
+            raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
+
+        output = msda_apply(value, spatial_shapes, level_start_index, loc, weights, self.im2col_step)
+        # mean over the queue (:255-261): [bs*Qn, nq, C] -> [bs, nq, C]
+        output = output.view(bs, Qn, num_query, embed_dims).mean(1)
+        output = self.output_proj(output)
+        if not self.batch_first:
+            output = output.permute(1, 0, 2)
+        return self.dropout(output) + identity
+
+
+@ATTENTION.register_module()
+class PredictionMSDeformableAttention(BaseModule):
+    """Deformable attention of the future-BEV decoder (vidar_decoder.py:289-516): self-attention
+    on the query BEV or cross-attention to the stacked history BEVs (one 'level' per frame)."""
+
+    def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=4, im2col_step=64,
+                 dropout=0.1, batch_first=True, norm_cfg=None, init_cfg=None):
+        super().__init__(init_cfg)
+        _check_heads(embed_dims, num_heads)
+        self.norm_cfg = norm_cfg
+        self.dropout = nn.Dropout(dropout)
+        self.batch_first = batch_first
+        self.fp16_enabled = False
+        self.im2col_step = im2col_step
+        self.embed_dims = embed_dims
+        self.num_levels = num_levels
+        self.num_heads = num_heads
+        self.num_points = num_points
+        self.sampling_offsets = nn.Linear(embed_dims, num_heads * num_levels * num_points * 2)
+        self.attention_weights = nn.Linear(embed_dims, num_heads * num_levels * num_points)
+        self.value_proj = nn.Linear(embed_dims, embed_dims)
+        self.output_proj = nn.Linear(embed_dims, embed_dims)
+        self.init_weights()
+
+    def init_weights(self):
+        constant_init(self.sampling_offsets, 0.)
+        self.sampling_offsets.bias.data = _ring_offsets(self.num_heads, self.num_levels, self.num_points)
+        constant_init(self.attention_weights, val=0., bias=0.)
+        xavier_init(self.value_proj, distribution="uniform", bias=0.)
+        xavier_init(self.output_proj, distribution="uniform", bias=0.)
+        self._is_init = True
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None,
+                key_padding_mask=None, reference_points=None, spatial_shapes=None,
+                level_start_index=None, flag="decoder", **kwargs):
+        if value is None:
+            value = query
+        if identity is None:
+            identity = query
+        if query_pos is not None:
+            query = query + query_pos
+        bs, num_query, _ = query.shape
+        num_value = value.shape[1]
+        assert (spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum() == num_value
+        H, L, P = self.num_heads, self.num_levels, self.num_points
+
+        value = self.value_proj(value)
+        if key_padding_mask is not None:
+            value = value.masked_fill(key_padding_mask[..., None], 0.0)
+        value = value.view(bs, num_value, H, -1)
+        offsets = self.sampling_offsets(query).view(bs, num_query, H, L, P, 2)
+        weights = self.attention_weights(query).view(bs, num_query, H, L * P).softmax(-1)
+        weights = weights.view(bs, num_query, H, L, P)
+        if reference_points.shape[-1] == 2:
+            loc = reference_points[:, :, None, :, None, :] + offsets / _wh(spatial_shapes)[None, None, None, :, None, :]
+        elif reference_points.shape[-1] == 4:
+            loc = (reference_points[:, :, None, :, None, :2]
+                   + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5)
+        else:
+            raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
+
+        output = msda_apply(value, spatial_shapes, level_start_index, loc, weights, self.im2col_step)
+        output = self.output_proj(output)
+        if not self.batch_first:
+            output = output.permute(1, 0, 2)
+        return self.dropout(output) + identity

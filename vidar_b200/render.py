@@ -46,7 +46,9 @@ def _check(sigma, origin, points, tindex, **extra):
     return N, M, T, To, Z, Y, X
 
 
-def _call(fn, device, *args):
+def _call(fn, device, *args, rays=1):
+    if rays == 0:       # empty ray set: outputs keep their initial values (null data_ptr)
+        return
     with torch.cuda.device(device):
         _lib.check(fn(*args, _lib.stream_ptr(device)))
 
@@ -60,7 +62,7 @@ def init(points, tindex, grid):
     if points.dtype != torch.float32 or tindex.dtype != torch.float32:
         raise RuntimeError("points / tindex must be float32")
     _call(_lib.lib().vidar_dvr_init, points.device, _lib.ptr(points), _lib.ptr(tindex),
-          _lib.ptr(occ), N, M, T, Z, Y, X)
+          _lib.ptr(occ), N, M, T, Z, Y, X, rays=M)
     return occ
 
 
@@ -74,7 +76,7 @@ def render_forward(sigma, origin, points, tindex, grid, phase_name):
     gt = torch.full((N, M), -1.0, dtype=torch.float32, device=sigma.device)
     _call(_lib.lib().vidar_dvr_render_forward, sigma.device, _lib.ptr(sigma), _lib.ptr(origin),
           _lib.ptr(points), _lib.ptr(tindex), _lib.ptr(pred), _lib.ptr(gt),
-          N, M, T, To, Z, Y, X, _PHASE[phase_name])
+          N, M, T, To, Z, Y, X, _PHASE[phase_name], rays=M)
     return [pred, gt]
 
 
@@ -88,7 +90,7 @@ def render(sigma, origin, points, tindex, loss_name):
     grad_sigma = torch.zeros_like(sigma)
     _call(_lib.lib().vidar_dvr_render, sigma.device, _lib.ptr(sigma), _lib.ptr(origin),
           _lib.ptr(points), _lib.ptr(tindex), _lib.ptr(pred), _lib.ptr(gt), _lib.ptr(grad_sigma),
-          N, M, T, To, Z, Y, X, _LOSS[loss_name])
+          N, M, T, To, Z, Y, X, _LOSS[loss_name], rays=M)
     return [pred, gt, grad_sigma]
 
 
@@ -109,12 +111,12 @@ def _dvxlr_render(sigma, origin, points, tindex, sigma_regul=None, lists=True, m
     if not lists and sigma_regul is None:
         _call(_lib.lib().vidar_dvxlr_forward, dev, _lib.ptr(sigma), _lib.ptr(origin),
               _lib.ptr(points), _lib.ptr(tindex), _lib.ptr(pred), _lib.ptr(gt),
-              N, M, T, To, Z, Y, X)
+              N, M, T, To, Z, Y, X, rays=M)
     else:
         _call(_lib.lib().vidar_dvxlr_render, dev, _lib.ptr(sigma), _lib.ptr(origin),
               _lib.ptr(points), _lib.ptr(tindex), _lib.ptr(sigma_regul), _lib.ptr(pred),
               _lib.ptr(gt), _lib.ptr(dd), _lib.ptr(idx), _lib.ptr(ray_pred), _lib.ptr(indicator),
-              N, M, T, To, Z, Y, X, max_d)
+              N, M, T, To, Z, Y, X, max_d, rays=M)
     return pred, gt, dd, idx, ray_pred, indicator
 
 
@@ -144,7 +146,7 @@ def _get_grad_sigma(elementwise_mult, indices, tindex, sigma_shape, indicator=No
     g2 = torch.zeros_like(sigma_shape) if indicator is not None else None
     _call(_lib.lib().vidar_dvxlr_get_grad_sigma, sigma_shape.device, _lib.ptr(elementwise_mult),
           _lib.ptr(indices), _lib.ptr(tindex), _lib.ptr(indicator), _lib.ptr(grad_ray_pred),
-          _lib.ptr(g), _lib.ptr(g2), N, M, T, Z, Y, X, max_d)
+          _lib.ptr(g), _lib.ptr(g2), N, M, T, Z, Y, X, max_d, rays=M)
     return [g] if g2 is None else [g, g2]
 
 
@@ -170,7 +172,7 @@ def _backward_fused(sigma, origin, points, tindex, grad_pred, grad_ray_pred=None
         grad_ray_pred = grad_ray_pred.float().contiguous()
     _call(_lib.lib().vidar_dvxlr_backward_fused, sigma.device, _lib.ptr(sigma), _lib.ptr(origin),
           _lib.ptr(points), _lib.ptr(tindex), _lib.ptr(grad_pred), _lib.ptr(grad_ray_pred),
-          _lib.ptr(grad_sigma), _lib.ptr(grad_regul), N, M, T, To, Z, Y, X, max_d)
+          _lib.ptr(grad_sigma), _lib.ptr(grad_regul), N, M, T, To, Z, Y, X, max_d, rays=M)
     return grad_sigma, grad_regul
 
 
