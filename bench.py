@@ -262,6 +262,11 @@ def run_ours(args):
     ms_step = total_ms / args.steps
     parts = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, n in enumerate(names)}
 
+    if os.environ.get("VIDAR_BENCH_PROFILE") == "1":   # under ncu: kernels only
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "ms_per_step": ms_step, "breakdown_ms": parts}))
+        return
+
     # ---- end-to-end through the plugin API with HOST buffers (pinned), copies timed
     e2e = None
     host_in = []

@@ -27,6 +27,11 @@ TARGETS = {
     "ref_dvxlr": ("dvxlr", ["dvxlr.cpp", "dvxlr.cu"]),
     "ref_dvxlr_v2": ("dvxlr", ["dvxlr_v2.cpp", "dvxlr_v2.cu"]),
 }
+# dvr.cu launches 1024-thread blocks (dvr.cu:345,651); built for sm_100a its render kernels
+# need > 64 registers/thread, and 1024 x 65+ exceeds the 64K-register file: every launch
+# fails with cudaErrorLaunchOutOfResources on a B200 (observed).  A register cap is the
+# build flag that makes the unmodified kernel launchable; it changes no arithmetic.
+EXTRA_FLAGS = {"ref_dvr": ["-maxrregcount=64"]}
 
 
 def _patch(text):
@@ -66,7 +71,8 @@ def build(names=None, force=False):
                 srcs.append(dst)
             cpp_extension.load(
                 name=name, sources=srcs, build_directory=bdir, verbose=False,
-                extra_cuda_cflags=["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"],
+                extra_cuda_cflags=["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"]
+                + EXTRA_FLAGS.get(name, []),
                 is_python_module=False)
             shutil.copy(os.path.join(bdir, name + ".so"), so_path(name))
             built[name] = so_path(name)

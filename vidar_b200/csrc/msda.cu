@@ -35,14 +35,17 @@ struct MsdaParams {
   const float* loc;
   const float* attn;
   int B, K, H, C, L, Q, P, LP;
-  int ipw;            // items (b,q,h) per warp
+  int ipw;            // items (b,q,h) per warp (vector kernels)
+  int lp_shift;       // log2(LP) when ipw > 1
+  int pix_stride;     // H*C floats between neighbouring pixels
   long long items;    // B*Q*H
 };
 
 // Decode one sample: pixel coordinates -> clamped base pixel, corner mask, fractions.
 // meta = mask(4b) | dx << 4 | dyW << 5 ; mask == 0 <=> sample contributes nothing.
 __device__ __forceinline__ void decode_sample(float lx, float ly, int Hl, int Wl, int start,
-                                              int& base, int& meta, float& lh, float& lw) {
+                                              int& base, int& meta, float& lh, float& lw,
+                                              int scale = 1) {
   // mmcv: h_im = loc_h * spatial_h - 0.5 (no fused multiply-add there either)
   const float h_im = __fsub_rn(__fmul_rn(ly, (float)Hl), 0.5f);
   const float w_im = __fsub_rn(__fmul_rn(lx, (float)Wl), 0.5f);
@@ -61,8 +64,9 @@ __device__ __forceinline__ void decode_sample(float lx, float ly, int Hl, int Wl
                      ((int)(h1 && w1) << 3);
     const int hl = max(h_low, 0), wl = max(w_low, 0);
     const int hh = min(h_low + 1, Hl - 1), wh = min(w_low + 1, Wl - 1);
-    base = start + hl * Wl + wl;
-    meta = mask | ((wh - wl) << 4) | (((hh - hl) * Wl) << 5);
+    // scale = 1: pixel units (generic kernels); scale = H*C: float offsets (vector kernels)
+    base = (start + hl * Wl + wl) * scale;
+    meta = mask | ((wh - wl) << 4) | (((hh - hl) * Wl * scale) << 5);
   }
 }
 
@@ -83,14 +87,16 @@ __device__ __forceinline__ float4 f4_scale(float s, const float4& v) {
 // Which (b,q,h) items does this warp own?  Returns false if none.
 //  ipw == 1 : block = 8 consecutive queries of one (b,h); blocks ordered (b, qtile, h).
 //  ipw  > 1 : ipw consecutive items in memory order (heads of the same query first).
+// All divisions happen here, once per warp -- never inside the sample loop.
 __device__ __forceinline__ bool warp_items(const MsdaParams& p, long long& item0) {
   const int warp = threadIdx.x >> 5;
   if (p.ipw == 1) {
-    const long long blk = blockIdx.x;
-    const int nqt = (p.Q + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int h = (int)(blk % p.H);
-    const int qt = (int)((blk / p.H) % nqt);
-    const int b = (int)(blk / ((long long)p.H * nqt));
+    const unsigned blk = blockIdx.x;
+    const unsigned nqt = (p.Q + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const unsigned h = blk % p.H;
+    const unsigned t = blk / p.H;
+    const unsigned qt = t % nqt;
+    const unsigned b = t / nqt;
     const int q = qt * kWarpsPerBlock + warp;
     if (q >= p.Q) return false;
     item0 = ((long long)b * p.Q + q) * p.H + h;
@@ -100,7 +106,31 @@ __device__ __forceinline__ bool warp_items(const MsdaParams& p, long long& item0
   return item0 < p.items;
 }
 
+// base pointer offset (floats) of item's (b, h) slab inside value / grad_value
+__device__ __forceinline__ size_t slab_offset(const MsdaParams& p, long long item64) {
+  const unsigned item = (unsigned)item64;            // items < 2^31 on the vector path
+  const unsigned qh = (unsigned)p.Q * (unsigned)p.H;
+  const unsigned b = item / qh;
+  const unsigned h = item % (unsigned)p.H;
+  return (size_t)b * p.K * p.pix_stride + (size_t)h * p.C;
+}
+
 template <int CV>
+__device__ __forceinline__ void store_item(const MsdaParams& p, float* __restrict__ out,
+                                           long long item, float4 acc, int g, int cl) {
+#pragma unroll
+  for (int off = CV; off < 32; off <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+  }
+  if (g == 0 && item < p.items)
+    *reinterpret_cast<float4*>(out + (size_t)item * p.C + cl * 4) = acc;
+}
+
+// MULTI = several items per warp (L*P a power of two < 32, one 32-sample chunk).
+template <int CV, bool MULTI>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
   constexpr int NG = 32 / CV;       // sample groups per warp
@@ -111,89 +141,75 @@ msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
   long long item0;
   if (!warp_items(p, item0)) return;
 
-  const int span = p.ipw * p.LP;                       // samples owned by this warp
-  const int nchunks = (span + 31) >> 5;
-  const size_t pix_stride = (size_t)p.H * p.C;         // floats between pixels
+  const int span = MULTI ? 32 : p.LP;                  // samples owned by this warp
+  const int nchunks = MULTI ? 1 : (span + 31) >> 5;
   const float* loc0 = p.loc + (size_t)item0 * p.LP * 2;
   const float* att0 = p.attn + (size_t)item0 * p.LP;
-  const int items_per_iter_den = p.LP;                 // sample -> item_local = s / LP
+  const float* vb = p.value + slab_offset(p, item0) + cl * 4;   // moves with the item (MULTI)
+  const unsigned pix = (unsigned)p.pix_stride;
 
   float4 acc = f4_zero();
-  int cur_item = 0;  // item_local the accumulator belongs to (warp-uniform)
-
   for (int chunk = 0; chunk < nchunks; ++chunk) {
-    // ---- lane j decodes sample j of the chunk
+    // ---- lane j decodes sample j of the chunk; weights are pre-multiplied by attention
     const int s = chunk * 32 + lane;
     int base = 0, meta = 0;
-    float lh = 0.f, lw = 0.f, aw = 0.f;
-    if (s < span && item0 + s / items_per_iter_den < p.items) {
+    float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
+    const bool live = MULTI ? (item0 + (s >> p.lp_shift) < p.items) : (s < span);
+    if (live) {
       const float2 xy = __ldg(reinterpret_cast<const float2*>(loc0) + s);
-      aw = __ldg(att0 + s);
-      const int l = (s % p.LP) / p.P;
+      const float aw = __ldg(att0 + s);
+      const int sl = MULTI ? (s & (p.LP - 1)) : s;
+      const int l = sl / p.P;
       const int Hl = (int)__ldg(p.shapes + 2 * l), Wl = (int)__ldg(p.shapes + 2 * l + 1);
-      decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw);
+      float lh, lw;
+      decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw, p.pix_stride);
+      const float hh = 1.f - lh, hw = 1.f - lw;
+      // invalid corners get weight 0; their (clamped) address aliases a valid corner's pixel
+      w1 = (meta & 1) ? aw * (hh * hw) : 0.f;
+      w2 = (meta & 2) ? aw * (hh * lw) : 0.f;
+      w3 = (meta & 4) ? aw * (lh * hw) : 0.f;
+      w4 = (meta & 8) ? aw * (lh * lw) : 0.f;
     }
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
-      const int slot0 = chunk * 32 + it * NG;  // first sample of this iteration (uniform)
-      if (slot0 >= span) break;
-      const int item_local = slot0 / p.LP;
-      if (item_local != cur_item) {
-        // flush finished item: sum the NG partial accumulators, group 0 stores
-#pragma unroll
-        for (int off = CV; off < 32; off <<= 1) {
-          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-          acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
-          acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
-        }
-        const long long item = item0 + cur_item;
-        if (g == 0 && item < p.items)
-          *reinterpret_cast<float4*>(out + (size_t)item * p.C + cl * 4) = acc;
-        acc = f4_zero();
-        cur_item = item_local;
-      }
+      if (!MULTI && chunk * 32 + it * NG >= span) break;
       const int src = it * NG + g;
       const int sbase = __shfl_sync(0xffffffffu, base, src);
       const int smeta = __shfl_sync(0xffffffffu, meta, src);
-      const float slh = __shfl_sync(0xffffffffu, lh, src);
-      const float slw = __shfl_sync(0xffffffffu, lw, src);
-      const float saw = __shfl_sync(0xffffffffu, aw, src);
-      const int mask = smeta & 15;
-      if (mask) {
-        const long long item = item0 + item_local;
-        const int h = (int)(item % p.H);
-        const int b = (int)(item / ((long long)p.Q * p.H));
-        const float* vb = p.value + ((size_t)b * p.K * p.H + h) * p.C + cl * 4;
-        const size_t dx = (size_t)((smeta >> 4) & 1) * pix_stride;
-        const size_t dy = (size_t)(smeta >> 5) * pix_stride;
-        const float* p1 = vb + (size_t)sbase * pix_stride;
-        float4 v1 = f4_zero(), v2 = f4_zero(), v3 = f4_zero(), v4 = f4_zero();
-        if (mask & 1) v1 = ldg4(p1);
-        if (mask & 2) v2 = ldg4(p1 + dx);
-        if (mask & 4) v3 = ldg4(p1 + dy);
-        if (mask & 8) v4 = ldg4(p1 + dy + dx);
-        const float hh = 1.f - slh, hw = 1.f - slw;
-        f4_fma(acc, saw * (hh * hw), v1);
-        f4_fma(acc, saw * (hh * slw), v2);
-        f4_fma(acc, saw * (slh * hw), v3);
-        f4_fma(acc, saw * (slh * slw), v4);
+      const float a1 = __shfl_sync(0xffffffffu, w1, src);
+      const float a2 = __shfl_sync(0xffffffffu, w2, src);
+      const float a3 = __shfl_sync(0xffffffffu, w3, src);
+      const float a4 = __shfl_sync(0xffffffffu, w4, src);
+      if (MULTI && it > 0 && ((it * NG) & (p.LP - 1)) == 0) {
+        // item changes every LP/NG iterations: flush the finished one, move the slab pointer
+        const int il = (it * NG) >> p.lp_shift;
+        store_item<CV>(p, out, item0 + il - 1, acc, g, cl);
+        acc = f4_zero();
+        vb = p.value + slab_offset(p, item0 + il) + cl * 4;
+      }
+      const float* vbi = vb;
+      asm volatile("" : "+l"(vbi));   // keep the slab base in a 64-bit register pair
+      if (smeta & 15) {
+        // four independent 16-byte loads, issued back to back (32-bit offsets, 64-bit base)
+        const unsigned o1 = (unsigned)sbase;                       // float offsets inside the slab
+        const unsigned o2 = o1 + ((smeta & 16) ? pix : 0u);
+        const unsigned o3 = o1 + (unsigned)(smeta >> 5);
+        const unsigned o4 = o3 + (o2 - o1);
+        const float4 v1 = ldg4(vbi + o1);
+        const float4 v2 = ldg4(vbi + o2);
+        const float4 v3 = ldg4(vbi + o3);
+        const float4 v4 = ldg4(vbi + o4);
+        f4_fma(acc, a1, v1);
+        f4_fma(acc, a2, v2);
+        f4_fma(acc, a3, v3);
+        f4_fma(acc, a4, v4);
       }
     }
   }
-#pragma unroll
-  for (int off = CV; off < 32; off <<= 1) {
-    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
-    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
-  }
-  const long long item = item0 + cur_item;
-  if (g == 0 && item < p.items)
-    *reinterpret_cast<float4*>(out + (size_t)item * p.C + cl * 4) = acc;
+  store_item<CV>(p, out, MULTI ? item0 + p.ipw - 1 : item0, acc, g, cl);
 }
 
-template <int CV>
+template <int CV, bool MULTI>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
                      float* __restrict__ grad_value, float* __restrict__ grad_loc,
@@ -206,97 +222,113 @@ msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
   long long item0;
   if (!warp_items(p, item0)) return;
 
-  const int span = p.ipw * p.LP;
-  const int nchunks = (span + 31) >> 5;
-  const size_t pix_stride = (size_t)p.H * p.C;
+  const int span = MULTI ? 32 : p.LP;
+  const int nchunks = MULTI ? 1 : (span + 31) >> 5;
   const float* loc0 = p.loc + (size_t)item0 * p.LP * 2;
   const float* att0 = p.attn + (size_t)item0 * p.LP;
   float* gloc0 = grad_loc + (size_t)item0 * p.LP * 2;
   float* gatt0 = grad_attn + (size_t)item0 * p.LP;
-
-  int cur_item = -1;
+  const unsigned pix = (unsigned)p.pix_stride;
+  size_t slab = slab_offset(p, item0) + cl * 4;
   float4 go = f4_zero();
+  if (!MULTI) go = ldg4(grad_out + (size_t)item0 * p.C + cl * 4);
 
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     const int s = chunk * 32 + lane;
     int base = 0, meta = 0;
     float lh = 0.f, lw = 0.f, aw = 0.f, fH = 0.f, fW = 0.f;
-    if (s < span && item0 + s / p.LP < p.items) {
+    float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
+    const bool live = MULTI ? (item0 + (s >> p.lp_shift) < p.items) : (s < span);
+    if (live) {
       const float2 xy = __ldg(reinterpret_cast<const float2*>(loc0) + s);
       aw = __ldg(att0 + s);
-      const int l = (s % p.LP) / p.P;
+      const int sl = MULTI ? (s & (p.LP - 1)) : s;
+      const int l = sl / p.P;
       const int Hl = (int)__ldg(p.shapes + 2 * l), Wl = (int)__ldg(p.shapes + 2 * l + 1);
-      decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw);
+      decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw, p.pix_stride);
       fH = (float)Hl;
       fW = (float)Wl;
+      const float hh = 1.f - lh, hw = 1.f - lw;
+      w1 = (meta & 1) ? aw * (hh * hw) : 0.f;
+      w2 = (meta & 2) ? aw * (hh * lw) : 0.f;
+      w3 = (meta & 4) ? aw * (lh * hw) : 0.f;
+      w4 = (meta & 8) ? aw * (lh * lw) : 0.f;
     }
+    float r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;   // this lane's sample: sum_c g*v_k
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
-      const int slot0 = chunk * 32 + it * NG;
-      if (slot0 >= span) break;
-      const int item_local = slot0 / p.LP;
-      const long long item = item0 + item_local;
-      if (item >= p.items) break;
-      const int h = (int)(item % p.H);
-      const int b = (int)(item / ((long long)p.Q * p.H));
-      if (item_local != cur_item) {
-        cur_item = item_local;
-        go = ldg4(grad_out + (size_t)item * p.C + cl * 4);
-      }
+      if (!MULTI && chunk * 32 + it * NG >= span) break;
       const int src = it * NG + g;
       const int sbase = __shfl_sync(0xffffffffu, base, src);
       const int smeta = __shfl_sync(0xffffffffu, meta, src);
-      const float slh = __shfl_sync(0xffffffffu, lh, src);
-      const float slw = __shfl_sync(0xffffffffu, lw, src);
-      const float saw = __shfl_sync(0xffffffffu, aw, src);
-      const float sH = __shfl_sync(0xffffffffu, fH, src);
-      const float sW = __shfl_sync(0xffffffffu, fW, src);
-      const int mask = smeta & 15;
-      float ga = 0.f, gx = 0.f, gy = 0.f;
-      if (mask) {
-        const size_t off0 = ((size_t)b * p.K * p.H + h) * p.C + cl * 4 + (size_t)sbase * pix_stride;
-        const size_t dx = (size_t)((smeta >> 4) & 1) * pix_stride;
-        const size_t dy = (size_t)(smeta >> 5) * pix_stride;
-        float4 v1 = f4_zero(), v2 = f4_zero(), v3 = f4_zero(), v4 = f4_zero();
-        if (mask & 1) v1 = ldg4(p.value + off0);
-        if (mask & 2) v2 = ldg4(p.value + off0 + dx);
-        if (mask & 4) v3 = ldg4(p.value + off0 + dy);
-        if (mask & 8) v4 = ldg4(p.value + off0 + dy + dx);
-        const float hh = 1.f - slh, hw = 1.f - slw;
-        const float w1 = hh * hw, w2 = hh * slw, w3 = slh * hw, w4 = slh * slw;
-        // grad_value: top_grad * attn * corner weight, 16-byte vector reductions
-        if (mask & 1) red_add_v4(grad_value + off0, f4_scale(saw * w1, go));
-        if (mask & 2) red_add_v4(grad_value + off0 + dx, f4_scale(saw * w2, go));
-        if (mask & 4) red_add_v4(grad_value + off0 + dy, f4_scale(saw * w3, go));
-        if (mask & 8) red_add_v4(grad_value + off0 + dy + dx, f4_scale(saw * w4, go));
-        const float d1 = f4_dot(go, v1), d2 = f4_dot(go, v2);
-        const float d3 = f4_dot(go, v3), d4 = f4_dot(go, v4);
-        ga = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;
-        gx = sW * saw * (hh * (d2 - d1) + slh * (d4 - d3));
-        gy = sH * saw * (hw * (d3 - d1) + slw * (d4 - d2));
-      }
-      // ---- transposed reduction of (ga, gx, gy, 0) over the CV lanes of the group
-      {
-        const bool up1 = (cl & (CV / 2)) != 0;
-        const float s0 = up1 ? ga : gy;
-        const float s1 = up1 ? gx : 0.f;
-        const float r0 = __shfl_xor_sync(0xffffffffu, s0, CV / 2);
-        const float r1 = __shfl_xor_sync(0xffffffffu, s1, CV / 2);
-        const float k0 = (up1 ? gy : ga) + r0;    // lower half: ga   upper half: gy
-        const float k1 = (up1 ? 0.f : gx) + r1;   // lower half: gx   upper half: 0
-        const bool up2 = (cl & (CV / 4)) != 0;
-        const float sb = up2 ? k0 : k1;
-        const float rb = __shfl_xor_sync(0xffffffffu, sb, CV / 4);
-        float k = (up2 ? k1 : k0) + rb;  // (0,0): ga  (0,1): gx  (1,0): gy  (1,1): 0
-#pragma unroll
-        for (int off = CV / 8; off >= 1; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
-        const int sidx = chunk * 32 + src;  // sample index inside the warp span
-        if (sidx < span) {
-          if (cl == 0) gatt0[sidx] = k;
-          else if (cl == CV / 4) gloc0[2 * sidx] = k;
-          else if (cl == CV / 2) gloc0[2 * sidx + 1] = k;
+      const float a1 = __shfl_sync(0xffffffffu, w1, src);
+      const float a2 = __shfl_sync(0xffffffffu, w2, src);
+      const float a3 = __shfl_sync(0xffffffffu, w3, src);
+      const float a4 = __shfl_sync(0xffffffffu, w4, src);
+      if (MULTI && ((it * NG) & (p.LP - 1)) == 0) {
+        const long long item = item0 + ((it * NG) >> p.lp_shift);
+        if (item < p.items) {
+          slab = slab_offset(p, item) + cl * 4;
+          go = ldg4(grad_out + (size_t)item * p.C + cl * 4);
+        } else {
+          go = f4_zero();
         }
       }
+      float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
+      if (smeta & 15) {
+        const unsigned o1 = (unsigned)sbase;                       // float offsets inside the slab
+        const unsigned o2 = o1 + ((smeta & 16) ? pix : 0u);
+        const unsigned o3 = o1 + (unsigned)(smeta >> 5);
+        const unsigned o4 = o3 + (o2 - o1);
+        const float* vs = p.value + slab;
+        float* gs = grad_value + slab;
+        asm volatile("" : "+l"(vs), "+l"(gs));
+        const float4 v1 = ldg4(vs + o1);
+        const float4 v2 = ldg4(vs + o2);
+        const float4 v3 = ldg4(vs + o3);
+        const float4 v4 = ldg4(vs + o4);
+        // grad_value: top_grad * attn * corner weight as 16-byte vector reductions.  An
+        // out-of-image corner has weight 0 and aliases a valid pixel: its reduction adds 0.
+        red_add_v4(gs + o1, f4_scale(a1, go));
+        red_add_v4(gs + o2, f4_scale(a2, go));
+        red_add_v4(gs + o3, f4_scale(a3, go));
+        red_add_v4(gs + o4, f4_scale(a4, go));
+        d1 = f4_dot(go, v1); d2 = f4_dot(go, v2); d3 = f4_dot(go, v3); d4 = f4_dot(go, v4);
+      }
+      // ---- transposed reduction of (d1..d4) over the CV lanes of the group: 4 shuffles;
+      //      afterwards lane class (cl & CV/2, cl & CV/4) = (0,0):d1 (0,1):d2 (1,0):d3 (1,1):d4
+      const bool up1 = (cl & (CV / 2)) != 0;
+      const float e0 = __shfl_xor_sync(0xffffffffu, up1 ? d1 : d3, CV / 2);
+      const float e1 = __shfl_xor_sync(0xffffffffu, up1 ? d2 : d4, CV / 2);
+      const float k0 = (up1 ? d3 : d1) + e0;    // lower half: d1   upper half: d3
+      const float k1 = (up1 ? d4 : d2) + e1;    // lower half: d2   upper half: d4
+      const bool up2 = (cl & (CV / 4)) != 0;
+      const float eb = __shfl_xor_sync(0xffffffffu, up2 ? k0 : k1, CV / 4);
+      float k = (up2 ? k1 : k0) + eb;
+#pragma unroll
+      for (int off = CV / 8; off >= 1; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
+      // ---- hand the four sums back to the lane that decoded the sample (lane it*NG + g')
+      const int back = (lane & (NG - 1)) * CV;
+      const float t1 = __shfl_sync(0xffffffffu, k, back);
+      const float t2 = __shfl_sync(0xffffffffu, k, back + CV / 4);
+      const float t3 = __shfl_sync(0xffffffffu, k, back + CV / 2);
+      const float t4 = __shfl_sync(0xffffffffu, k, back + CV / 2 + CV / 4);
+      if ((lane / NG) == it) { r1 = t1; r2 = t2; r3 = t3; r4 = t4; }
+    }
+    // ---- every lane finishes its own sample; coalesced stores
+    if (live) {
+      const float hh = 1.f - lh, hw = 1.f - lw;
+      // an out-of-image corner contributes v = 0 to every gradient (mmcv col2im_bilinear)
+      if (!(meta & 1)) r1 = 0.f;
+      if (!(meta & 2)) r2 = 0.f;
+      if (!(meta & 4)) r3 = 0.f;
+      if (!(meta & 8)) r4 = 0.f;
+      const bool ok = (meta & 15) != 0;
+      const float ga = ok ? (hh * hw) * r1 + (hh * lw) * r2 + (lh * hw) * r3 + (lh * lw) * r4 : 0.f;
+      const float gx = ok ? fW * aw * (hh * (r2 - r1) + lh * (r4 - r3)) : 0.f;
+      const float gy = ok ? fH * aw * (hw * (r3 - r1) + lw * (r4 - r2)) : 0.f;
+      gatt0[s] = ga;
+      reinterpret_cast<float2*>(gloc0)[s] = make_float2(gx, gy);
     }
   }
 }
@@ -392,16 +424,28 @@ int fill_params(MsdaParams& p, const float* value, const int64_t* shapes, const 
   p.LP = L * P;
   p.items = (long long)B * Q * H;
   p.ipw = 1;
+  p.lp_shift = 0;
+  p.pix_stride = H * C;
   return VIDAR_OK;
 }
 
-inline bool vec_ok(int C) { return C == 16 || C == 32 || C == 64; }
+inline int pick_ipw(int LP, int CV);
+// vector kernels: C in {16,32,64}, 32-bit intra-batch offsets and item counts
+inline bool vec_ok(const MsdaParams& p) {
+  return (p.C == 16 || p.C == 32 || p.C == 64) && (long long)p.K * p.H * p.C < (1LL << 26) &&   /* offsets ride in meta >> 5 */
+         p.items < (1LL << 31) && (long long)p.Q * p.H < (1LL << 31);
+}
+inline void set_ipw(MsdaParams& p, int CV) {
+  p.ipw = pick_ipw(p.LP, CV);
+  p.lp_shift = 0;
+  while ((1 << p.lp_shift) < p.LP) ++p.lp_shift;
+}
 
 // items per warp for the vector kernels: pack several (b,q,h) into one 32-sample chunk
 // when L*P is small (temporal self-attention: L*P = 4).
 inline int pick_ipw(int LP, int CV) {
   const int NG = 32 / CV;
-  if (LP < 32 && 32 % LP == 0 && LP % NG == 0) return 32 / LP;
+  if (LP >= 2 && LP < 32 && 32 % LP == 0 && LP % NG == 0) return 32 / LP;
   return 1;
 }
 
@@ -429,15 +473,19 @@ extern "C" int vidar_msda_forward(const float* value, const int64_t* spatial_sha
   if (rc) return rc;
   VIDAR_REQUIRE(out, "ms_deform_attn_forward: null output");
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec_ok(C)) {
+  if (vec_ok(p)) {
     const int CV = C / 4;
-    p.ipw = pick_ipw(p.LP, CV);
+    set_ipw(p, CV);
     const long long nb = num_blocks(p);
     VIDAR_REQUIRE(nb < 2147483647LL, "ms_deform_attn_forward: problem too large");
     const dim3 grid((unsigned)nb), block(kWarpsPerBlock * 32);
-    if (CV == 8) msda_forward_kernel<8><<<grid, block, 0, st>>>(p, out);
-    else if (CV == 4) msda_forward_kernel<4><<<grid, block, 0, st>>>(p, out);
-    else msda_forward_kernel<16><<<grid, block, 0, st>>>(p, out);
+#define VIDAR_FWD(CVV)                                                            \
+  if (p.ipw > 1) msda_forward_kernel<CVV, true><<<grid, block, 0, st>>>(p, out);  \
+  else msda_forward_kernel<CVV, false><<<grid, block, 0, st>>>(p, out)
+    if (CV == 8) { VIDAR_FWD(8); }
+    else if (CV == 4) { VIDAR_FWD(4); }
+    else { VIDAR_FWD(16); }
+#undef VIDAR_FWD
   } else {
     const long long n = p.items * C;
     const long long nb = (n + 255) / 256;
@@ -460,18 +508,23 @@ extern "C" int vidar_msda_backward(const float* value, const int64_t* spatial_sh
   VIDAR_REQUIRE(grad_out && grad_value && grad_sampling_loc && grad_attn_weight,
                 "ms_deform_attn_backward: null gradient pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec_ok(C)) {
+  if (vec_ok(p)) {
     const int CV = C / 4;
-    p.ipw = pick_ipw(p.LP, CV);
+    set_ipw(p, CV);
     const long long nb = num_blocks(p);
     VIDAR_REQUIRE(nb < 2147483647LL, "ms_deform_attn_backward: problem too large");
     const dim3 grid((unsigned)nb), block(kWarpsPerBlock * 32);
-    if (CV == 8)
-      msda_backward_kernel<8><<<grid, block, 0, st>>>(p, grad_out, grad_value, grad_sampling_loc, grad_attn_weight);
-    else if (CV == 4)
-      msda_backward_kernel<4><<<grid, block, 0, st>>>(p, grad_out, grad_value, grad_sampling_loc, grad_attn_weight);
-    else
-      msda_backward_kernel<16><<<grid, block, 0, st>>>(p, grad_out, grad_value, grad_sampling_loc, grad_attn_weight);
+#define VIDAR_BWD(CVV)                                                                        \
+  if (p.ipw > 1)                                                                              \
+    msda_backward_kernel<CVV, true><<<grid, block, 0, st>>>(p, grad_out, grad_value,          \
+                                                            grad_sampling_loc, grad_attn_weight); \
+  else                                                                                        \
+    msda_backward_kernel<CVV, false><<<grid, block, 0, st>>>(p, grad_out, grad_value,         \
+                                                             grad_sampling_loc, grad_attn_weight)
+    if (CV == 8) { VIDAR_BWD(8); }
+    else if (CV == 4) { VIDAR_BWD(4); }
+    else { VIDAR_BWD(16); }
+#undef VIDAR_BWD
   } else {
     cudaError_t e = cudaMemsetAsync(grad_sampling_loc, 0, sizeof(float) * 2 * (size_t)p.items * p.LP, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(grad_attn_weight, 0, sizeof(float) * (size_t)p.items * p.LP, st);
