@@ -85,18 +85,21 @@ __device__ __forceinline__ float4 f4_scale(float s, const float4& v) {
 }
 
 // Which (b,q,h) items does this warp own?  Returns false if none.
-//  ipw == 1 : block = 8 consecutive queries of one (b,h); blocks ordered (b, qtile, h).
+//  ipw == 1 : block = 8 consecutive queries of one (b,h); blocks ordered (b, h, qtile).
 //  ipw  > 1 : ipw consecutive items in memory order (heads of the same query first).
 // All divisions happen here, once per warp -- never inside the sample loop.
 __device__ __forceinline__ bool warp_items(const MsdaParams& p, long long& item0) {
   const int warp = threadIdx.x >> 5;
   if (p.ipw == 1) {
+    // blocks ordered (b, h, qtile): at any moment the whole chip works on ONE (b, h) slab, so
+    // an SM's L1 holds a single head's coarse levels (15x25: 48 KB, 29x50: 186 KB) instead of
+    // thrashing between eight.
     const unsigned blk = blockIdx.x;
     const unsigned nqt = (p.Q + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const unsigned h = blk % p.H;
-    const unsigned t = blk / p.H;
-    const unsigned qt = t % nqt;
-    const unsigned b = t / nqt;
+    const unsigned qt = blk % nqt;
+    const unsigned t = blk / nqt;
+    const unsigned h = t % p.H;
+    const unsigned b = t / p.H;
     const int q = qt * kWarpsPerBlock + warp;
     if (q >= p.Q) return false;
     item0 = ((long long)b * p.Q + q) * p.H + h;
