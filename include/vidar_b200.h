@@ -161,6 +161,50 @@ int vidar_dvxlr_backward_fused(const float* sigma, const float* origin, const fl
                                int N, int M, int T, int To, int Z, int Y, int X, int max_d,
                                void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * (ii-b) ViDAR head: ray sampler, fused cross-entropy, arg-max decode
+ *   (projects/mmdet3d_plugin/bevformer/dense_heads/vidar_head_base.py:420-509, 586-592, 706-738)
+ *   sigma  [F, Z, Y, X]  the F frame volumes of one batch element
+ *   origin [F, 3], points [R, 3] (voxel units), frame [R] int32 frame of each ray (NULL = 0)
+ *   Per ray: sample 0 = the GT point (with_gt), then num_way waypoints at
+ *   o + u*(k+0.5)*step; K = num_way + with_gt samples; logit = trilinear grid_sample
+ *   (align_corners=False, zeros) or -inf where any normalised coordinate leaves (-1,1).
+ * ---------------------------------------------------------------------------------- */
+
+/* Materialising sampler = the per-(batch,frame) body of _get_grid_features (:433-500).
+ *   logits [R, K] (NULL = skip), length [R, K] |x-o| (NULL = skip),
+ *   valid [R] 1/0: GT point strictly inside the volume (:464) (NULL = skip). */
+int vidar_ray_sample(const float* sigma, const float* origin, const float* points,
+                     const int32_t* frame, float* logits, float* length, float* valid,
+                     int R, int F, int Z, int Y, int X, int num_way, float step, int with_gt,
+                     void* stream);
+
+/* Its backward: grad_sigma [F,Z,Y,X] (caller-zeroed) += trilinear scatter of grad_logits. */
+int vidar_ray_sample_backward(const float* origin, const float* points, const int32_t* frame,
+                              const float* grad_logits, float* grad_sigma,
+                              int R, int F, int Z, int Y, int X, int num_way, float step,
+                              int with_gt, void* stream);
+
+/* Fused sampler + F.cross_entropy(label 0) (:586-588): ce[r] = logsumexp(logits) - logit_0.
+ *   ce, lse, valid [R]; rays whose GT point is outside get ce = 0, valid = 0. */
+int vidar_ray_ce_forward(const float* sigma, const float* origin, const float* points,
+                         const int32_t* frame, float* ce, float* lse, float* valid,
+                         int R, int F, int Z, int Y, int X, int num_way, float step,
+                         void* stream);
+
+/* Backward of the fused CE: grad_sigma (caller-zeroed) += sum_r grad_ce[r] * d ce[r]/d sigma.
+ *   lse from the forward; grad_ce NULL = all ones. */
+int vidar_ray_ce_backward(const float* sigma, const float* origin, const float* points,
+                          const int32_t* frame, const float* lse, const float* grad_ce,
+                          float* grad_sigma, int R, int F, int Z, int Y, int X, int num_way,
+                          float step, void* stream);
+
+/* Inference decode (:706-732): exact zeros -> -inf, first arg-max over the num_way
+ * waypoints; depth [R] = its |x-o| (voxel units), index [R] (float, NULL = skip). */
+int vidar_ray_argmax(const float* sigma, const float* origin, const float* points,
+                     const int32_t* frame, float* depth, float* index,
+                     int R, int F, int Z, int Y, int X, int num_way, float step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,105 @@
+"""Per-op timings on one B200: this repo's kernels next to the reference's own PyTorch code
+run eagerly on the same GPU (test infrastructure; not the graded bench line).
+    python tools/bench_ops.py > gpurun_out/ops.json
+MSDA eager = the grid_sample formula of mmcv's multi_scale_deformable_attn_pytorch (oracle
+restatement) on CUDA; ray sampler+CE eager = oracle restatement of vidar_head_base.py on CUDA."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from oracle import msda_ref  # noqa: E402
+from vidar_b200 import msda, ray_head  # noqa: E402
+
+
+def timed(fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def main():
+    dev = torch.device("cuda:0")
+    out = {}
+    # ---- MSDA, one camera of the SCA workload
+    d = bench.sca_like_inputs(dev, cams=1)
+
+    def ours():
+        v = d["value"].requires_grad_(True)
+        o = msda.MultiScaleDeformableAttnFunction_fp32.apply(v, d["shapes"], d["lsi"], d["loc"].requires_grad_(True),
+                                                             d["attn"].requires_grad_(True), 64)
+        o.backward(d["grad_out"])
+
+    def eager():
+        v = d["value"].detach().requires_grad_(True)
+        o = msda_ref.msda_grid_sample(v, d["shapes"].cpu(), d["loc"].detach().requires_grad_(True),
+                                      d["attn"].detach().requires_grad_(True))
+        o.backward(d["grad_out"])
+
+    out["msda_1cam_40000q_fwd_bwd_ms"] = {"vidar_b200": timed(ours), "torch_eager_grid_sample": timed(eager, n=3, warm=1)}
+    # ---- TSA shape: B=2, 1 level 200x200, P=4
+    g = torch.Generator(device=dev).manual_seed(0)
+    val = torch.randn(2, 40000, 8, 32, device=dev, generator=g)
+    loc = torch.rand(2, 40000, 8, 1, 4, 2, device=dev, generator=g)
+    aw = torch.softmax(torch.randn(2, 40000, 8, 4, device=dev, generator=g), -1).view(2, 40000, 8, 1, 4)
+    shp = torch.tensor([[200, 200]], device=dev)
+    lsi = torch.tensor([0], device=dev)
+    go = torch.randn(2, 40000, 256, device=dev, generator=g)
+
+    def tsa():
+        v = val.detach().requires_grad_(True)
+        o = msda.MultiScaleDeformableAttnFunction_fp32.apply(v, shp, lsi, loc.detach().requires_grad_(True),
+                                                             aw.detach().requires_grad_(True), 64)
+        o.backward(go)
+
+    def tsa_eager():
+        v = val.detach().requires_grad_(True)
+        o = msda_ref.msda_grid_sample(v, shp.cpu(), loc.detach().requires_grad_(True), aw.detach().requires_grad_(True))
+        o.backward(go)
+    out["msda_tsa_B2_Q40000_fwd_bwd_ms"] = {"vidar_b200": timed(tsa), "torch_eager_grid_sample": timed(tsa_eager, n=3, warm=1)}
+
+    # ---- head ray sampler + CE: 3 frames 16x200x200, 30k rays, 512 waypoints
+    from tests.test_ray_head_gpu import _big_case
+    from oracle import ray_head_ref
+    sigma, origin, pts, frame = (t.to(dev) for t in _big_case(dev))
+
+    def ce_ours():
+        s = sigma.detach().requires_grad_(True)
+        ce, valid = ray_head.ray_ce(s, origin, pts, frame, 512, 1.0)
+        ce.sum().backward()
+
+    def ce_eager():
+        s = sigma.detach().requires_grad_(True)
+        tot = 0
+        for f in range(3):
+            sel = frame == f
+            lg, ln, vd = ray_head_ref.sample_frame(s[f], origin[f], pts[sel], 512, 1.0)
+            tot = tot - torch.log_softmax(lg[vd], -1)[:, 0].sum()
+        tot.backward()
+
+    import oracle.ray_head_ref as rr
+    _orig = rr.torch.tensor
+    out["ray_ce_30k_rays_512wp_fwd_bwd_ms"] = {"vidar_b200": timed(ce_ours)}
+    try:
+        torch.set_default_device(dev)
+        out["ray_ce_30k_rays_512wp_fwd_bwd_ms"]["torch_eager_reference_formula"] = timed(ce_eager, n=3, warm=1)
+    except Exception as e:
+        out["ray_ce_30k_rays_512wp_fwd_bwd_ms"]["torch_eager_reference_formula"] = f"failed: {e}"
+    finally:
+        torch.set_default_device("cpu")
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
