@@ -6,8 +6,11 @@ A "step" is one pass of ViDAR's two hot paths over one synthetic sample
   (i)  MSDA forward + backward at the SpatialCrossAttention shape: 6 cameras, 4-level FPN of a
        928x1600 input (30825 keys/cam), 200x200 = 40000 BEV queries per camera, 8 heads x 32
        channels, 8 sampling points per level (4 Z-anchors x 2);
-  (ii) voxel ray-caster forward + loss backward (`dvr.render`, L2): sigma [1,3,16,200,200],
-       30000 LiDAR-like rays over 3 frames.
+  (ii) LatentRendering module forward + backward on a [1,200,200,256] BEV embedding
+       (pred_height 16, 256 waypoints of step 0.5, sigmoid; three Linear layers + fused core);
+  (iii) ViDAR-head ray sampler + cross-entropy forward + backward: sigma [3,16,200,200], 30000
+       LiDAR-like rays over 3 frames, 512 waypoints + the GT sample per ray;
+  (iv) voxel ray-caster forward + loss backward (`dvr.render`, L2) on the same volume and rays.
 metric = rays/sec = 30000 rays / step time (whole job); ms_per_step is the same thing as time.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -33,9 +36,13 @@ import torch  # noqa: E402
 LEVELS = ((116, 200), (58, 100), (29, 50), (15, 25))
 NUM_CAMS, BEV_Q, HEADS, HEAD_DIM, POINTS = 6, 40000, 8, 32, 8
 RAYS, FRAMES, GRID = 30000, 3, (16, 200, 200)
-METRIC = "rays/sec (fwd+bwd step: 6-cam 200x200-BEV MSDA + 30k-ray voxel render)"
-WORKLOAD = ("configs[1]+[2]: MSDA fwd+bwd B=6 K=30825 Q=40000 H=8 C=32 L=4 P=8, then "
-            "dvr.render(l2) sigma[1,3,16,200,200] 30000 rays")
+WAYPOINTS, LR_GRID_NUM, EMBED = 512, 256, 256
+METRIC = "rays/sec (fwd+bwd step: 6-cam 200x200-BEV MSDA + latent rendering + 30k-ray head CE + voxel render)"
+WORKLOAD = ("configs[1]+[2]: MSDA fwd+bwd B=6 K=30825 Q=40000 H=8 C=32 L=4 P=8; LatentRendering fwd+bwd "
+            "embed[1,200,200,256] pred_height=16 grid_num=256; ray sampler+CE fwd+bwd sigma[3,16,200,200] "
+            "30000 rays x 513 samples; dvr.render(l2) sigma[1,3,16,200,200] 30000 rays")
+LR_CFG = dict(type="LatentRendering", embed_dims=EMBED, num_pred_fcs=0, pred_height=GRID[0],
+              grid_num=LR_GRID_NUM, grid_step=0.5, reduction=16, act="sigmoid")
 
 
 # ------------------------------------------------------------------------------------------
@@ -138,25 +145,15 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def shard_rows(rank, world, cams=NUM_CAMS, Q=BEV_Q):
-    """Contiguous share of the cams*Q (camera, query) rows -> [(cam, q0, q1), ...]."""
-    total = cams * Q
-    lo, hi = rank * total // world, (rank + 1) * total // world
-    segs = []
-    for c in range(cams):
-        a, b = max(lo, c * Q), min(hi, (c + 1) * Q)
-        if a < b:
-            segs.append((c, a - c * Q, b - c * Q))
-    return segs
-
-
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
 
-    from vidar_b200 import _lib, msda, render
+    from vidar_b200 import _lib, msda, ray_head, render, sharding
+    from vidar_b200.registry import build_attention
+    import vidar_b200.modules  # noqa: F401  (registers LatentRendering)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -170,7 +167,8 @@ def run_ours(args):
 
     # ---- device-resident inputs (this rank's shard)
     full = sca_like_inputs(dev)
-    segs = shard_rows(rank, world)
+    segs = sharding.shard_rows(rank, world, NUM_CAMS, BEV_Q)
+    cam_groups = sharding.camera_groups(world, NUM_CAMS, BEV_Q, rank) if world > 1 else {}
     my_cams = sorted({c for c, _, _ in segs})
     seg_in = []
     for c, q0, q1 in segs:
@@ -187,27 +185,31 @@ def run_ours(args):
     points = torch.from_numpy(points_np[:, r0:r1].copy()).to(dev)
     tindex = torch.from_numpy(tindex_np[:, r0:r1].copy()).to(dev)
     del full
+    # head ray sampler: same rays, per-frame volumes = sigma[0]; LatentRendering: replicated per rank
+    ce_points = points[0].contiguous()
+    ce_frame = tindex[0].to(torch.int32).contiguous()
+    ce_origin = origin[0].contiguous()
+    torch.manual_seed(0)
+    latent = build_attention(LR_CFG).to(dev)
+    lg = torch.Generator(device=dev).manual_seed(7)
+    embed = torch.randn(1, GRID[1], GRID[2], EMBED, device=dev, generator=lg)
+    grad_embed = torch.randn(1, GRID[1], GRID[2], EMBED, device=dev, generator=lg)
     grad_value = {c: torch.zeros(1, sum(h * w for h, w in LEVELS), HEADS, HEAD_DIM, device=dev) for c in my_cams}
-    max_rows = -(-NUM_CAMS * BEV_Q // world)
-    gather_buf = torch.empty(world, max_rows, HEADS * HEAD_DIM, device=dev) if world > 1 else None
-    out_pad = torch.zeros(max_rows, HEADS * HEAD_DIM, device=dev) if world > 1 else None
-    shares_camera = world > 1 and (NUM_CAMS % world != 0)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    names = ["msda_fwd", "msda_bwd", "render"]
+    names = ["msda_fwd", "msda_bwd", "latent_render", "ray_ce", "render"]
     marks = []
 
     def step(record):
-        e = [ev() for _ in range(4)] if record else None
+        e = [ev() for _ in range(6)] if record else None
         if record:
             e[0].record()
         outs = []
         for s in seg_in:
             outs.append(msda.ext_module.ms_deform_attn_forward(s["value"], shapes, lsi, s["loc"], s["attn"], im2col_step=64))
         if world > 1:   # the one exchange of the forward: every rank gets all BEV rows
-            o = torch.cat([x.view(-1, HEADS * HEAD_DIM) for x in outs], 0)
-            out_pad[:o.shape[0]] = o
-            dist.all_gather_into_tensor(gather_buf, out_pad)
+            bev_rows = sharding.gather_rows(torch.cat([x.view(-1, HEADS * HEAD_DIM) for x in outs], 0),
+                                            world, NUM_CAMS * BEV_Q)
         if record:
             e[1].record()
         for c in my_cams:
@@ -219,19 +221,29 @@ def run_ours(args):
             msda.ext_module.ms_deform_attn_backward(s["value"], shapes, lsi, s["loc"], s["attn"], s["grad_out"],
                                                     grad_value[s["cam"]], gl, ga, im2col_step=64)
             grads.append((gl, ga))
-        if shares_camera:   # a camera split over ranks: sum its partial grad_value
-            for c in range(NUM_CAMS):
-                if c in grad_value:
-                    dist.all_reduce(grad_value[c])
+        for c, grp in cam_groups.items():   # a camera split over ranks: sum its partial grad_value
+            dist.all_reduce(grad_value[c], group=grp)
         if record:
             e[2].record()
+        emb = embed.detach().requires_grad_(True)
+        latent.zero_grad(set_to_none=True)
+        latent(emb).backward(grad_embed)
+        if record:
+            e[3].record()
+        sg = sigma[0].detach().requires_grad_(True)
+        ce, valid = ray_head.ray_ce(sg, ce_origin, ce_points, ce_frame, WAYPOINTS, 1.0)
+        ce.sum().backward()
+        if world > 1:
+            dist.all_reduce(sg.grad)
+        if record:
+            e[4].record()
         pred, gt, grad_sigma = render.dvr.render(sigma, origin, points, tindex, "l2")
         if world > 1:
             dist.all_reduce(grad_sigma)
         if record:
-            e[3].record()
+            e[5].record()
             marks.append(e)
-        return outs, grads, pred, grad_sigma
+        return outs, grads, pred, grad_sigma, emb.grad, sg.grad
 
     def sync():
         torch.cuda.synchronize()
@@ -274,8 +286,10 @@ def run_ours(args):
         host_in.append({k: s[k].cpu().pin_memory() for k in ("value", "loc", "attn", "grad_out")})
     h_sigma, h_origin = sigma.cpu().pin_memory(), origin.cpu().pin_memory()
     h_points, h_tindex = points.cpu().pin_memory(), tindex.cpu().pin_memory()
+    h_embed, h_gembed = embed.cpu().pin_memory(), grad_embed.cpu().pin_memory()
     h2d = sum(t.numel() * 4 for h in host_in for t in h.values()) + 4 * (
-        h_sigma.numel() + h_origin.numel() + h_points.numel() + h_tindex.numel())
+        h_sigma.numel() + h_origin.numel() + h_points.numel() + h_tindex.numel()
+        + h_embed.numel() + h_gembed.numel())
     host_out = None
 
     def e2e_step():
@@ -294,6 +308,13 @@ def run_ours(args):
         pt = h_points.to(dev, non_blocking=True)
         ti = h_tindex.to(dev, non_blocking=True)
         d_out += render.dvr.render(sg, og, pt, ti, "l2")
+        emb = h_embed.to(dev, non_blocking=True).requires_grad_(True)
+        lo = latent(emb)
+        lo.backward(h_gembed.to(dev, non_blocking=True))
+        sg2 = sg[0].detach().requires_grad_(True)
+        ce, valid = ray_head.ray_ce(sg2, og[0].contiguous(), pt[0].contiguous(), ti[0].to(torch.int32), WAYPOINTS, 1.0)
+        ce.sum().backward()
+        d_out += [lo.detach(), emb.grad, ce.detach(), sg2.grad]
         if host_out is None:
             host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in d_out]
         for hbuf, t in zip(host_out, d_out):
@@ -318,7 +339,8 @@ def run_ours(args):
     d2h = sum(t.numel() * 4 for t in host_out)
     e2e = {"value": RAYS / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "api": "MultiScaleDeformableAttnFunction_fp32.apply+backward, dvr.render; pinned host tensors"}
+           "api": "MultiScaleDeformableAttnFunction_fp32.apply+backward, LatentRendering module, ray_head.ray_ce, "
+                  "dvr.render; pinned host tensors in, pinned host tensors out"}
 
     if rank != 0:
         if world > 1:
@@ -351,7 +373,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (seeded: perspective pillar fan per camera, LiDAR-like rays)",
         "config": {"workload": WORKLOAD, "l2_policy": "inputs larger than L2 (1.4 GB of MSDA operands per step)",
-                   "sharding": "rows of (camera,query) and rays split over ranks; all_gather(out), all_reduce(grad_sigma)"
+                   "sharding": "rows of (camera,query) and rays split over ranks; all_gather(MSDA out), "
+                               "all_reduce(grad_sigma); LatentRendering replicated per rank"
                    if world > 1 else "single GPU"},
         "breakdown_ms": parts, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
@@ -380,21 +403,65 @@ def _cpu_msda(d, q):
     return time.perf_counter() - t0
 
 
+CPU_LR_CELLS = 4000      # of 40000 BEV cells
+CPU_CE_RAYS = 6000       # of 30000 rays
+
+
+def _cpu_latent(lat):
+    """LatentRendering fwd+bwd on the first CPU_LR_CELLS cells (both phases; phase 2 samples a
+    full-size prob map); scaled by 40000/CPU_LR_CELLS."""
+    import types
+
+    import torch.nn.functional as F  # noqa: F401
+    from oracle import latent_render_ref as lr
+    occ, feat, probmap = lat
+    t0 = time.perf_counter()
+    o = occ.detach().requires_grad_(True)
+    f = feat.detach().requires_grad_(True)
+    p, q = lr.latent_core(o, f, LR_GRID_NUM, 0.5, 1e-3, "sigmoid", cells=slice(0, CPU_LR_CELLS), prob_map=probmap)
+    (p.sum() + q.sum()).backward()
+    return (time.perf_counter() - t0) * (GRID[1] * GRID[2] / CPU_LR_CELLS)
+
+
+def _cpu_ray_ce(rays):
+    from oracle import ray_head_ref as rr
+    sigma, origin, points, tindex = rays
+    t0 = time.perf_counter()
+    s = torch.from_numpy(sigma[0]).requires_grad_(True)
+    tot = 0
+    n = 0
+    for f in range(FRAMES):
+        sel = np.flatnonzero(tindex[0] == f)[: CPU_CE_RAYS // FRAMES]
+        lg, ln, vd = rr.sample_frame(s[f], torch.from_numpy(origin[0, f]), torch.from_numpy(points[0][sel]), WAYPOINTS, 1.0)
+        tot = tot - torch.log_softmax(lg[vd], -1)[:, 0].sum()
+        n += len(sel)
+    tot.backward()
+    return (time.perf_counter() - t0) * (RAYS / n)
+
+
 def cpu_step(inputs):
-    """One bounded sample.  MSDA fwd+bwd is timed on one camera at two query counts; the
-    affine fit t(Q) = a + b*Q gives the full step as 6*a + 240000*b (each camera pays the
-    per-call cost of touching its 31.6 MB value / grad_value once).  The ray-caster port runs
-    on all 30000 rays.  Returns (estimated seconds for the FULL step, sample seconds, dvr s)."""
+    """One bounded sample of every part of the step, extrapolated to the full step.
+      MSDA fwd+bwd: one camera at two query counts; affine fit t(Q) = a + b*Q -> 6*a + 240000*b
+        (each camera pays the per-call cost of touching its 31.6 MB value / grad_value once);
+      LatentRendering core fwd+bwd: CPU_LR_CELLS of the 40000 cells, scaled;
+      head ray sampler + CE fwd+bwd: CPU_CE_RAYS of the 30000 rays, scaled;
+      dvr.render: all 30000 rays (C/OpenMP port).
+    Returns (estimated seconds for the FULL step, sample seconds, per-part estimates)."""
     from oracle import dvr_ref
-    d, rays = inputs
+    d, rays, lat = inputs
+    t00 = time.perf_counter()
     ts = _cpu_msda(d, CPU_Q_SMALL)
     tl = _cpu_msda(d, CPU_Q_LARGE)
     b = max(tl - ts, 0.0) / (CPU_Q_LARGE - CPU_Q_SMALL)
     a = max(ts - b * CPU_Q_SMALL, 0.0)
+    t_msda = NUM_CAMS * a + NUM_CAMS * BEV_Q * b
+    t_lat = _cpu_latent(lat)
+    t_ce = _cpu_ray_ce(rays)
     t0 = time.perf_counter()
     dvr_ref.render(*rays, "l2")
     t_dvr = time.perf_counter() - t0
-    return NUM_CAMS * a + NUM_CAMS * BEV_Q * b + t_dvr, ts + tl, t_dvr
+    parts = {"msda": t_msda, "latent_render": t_lat, "ray_ce": t_ce, "dvr_render": t_dvr}
+    return t_msda + t_lat + t_ce + t_dvr, time.perf_counter() - t00, parts
 
 
 def cpu_inputs():
@@ -403,15 +470,21 @@ def cpu_inputs():
     d = dict(value=full["value"], shapes=full["shapes"], lsi=full["lsi"],
              loc=full["loc"][:, sl].contiguous(), attn=full["attn"][:, sl].contiguous(),
              grad_out=full["grad_out"][:, sl].contiguous())
-    return d, ray_inputs()
+    g = torch.Generator().manual_seed(3)
+    lat = (torch.randn(1, GRID[1], GRID[2], GRID[0], generator=g), torch.randn(1, GRID[1], GRID[2], GRID[0], generator=g),
+           torch.rand(1, GRID[1], GRID[2], GRID[0], generator=g))
+    return d, ray_inputs(), lat
 
 
 def _cpu_sample_text(est):
     from oracle import dvr_ref
-    return (f"per step: MSDA fwd+bwd (torch CPU grid_sample formula = the reference's CPU path) on 1 camera at "
-            f"{CPU_Q_SMALL} and {CPU_Q_LARGE} queries ({np.mean([e[1] for e in est]):.2f} s), affine fit "
-            f"extrapolated to 6 cams x 40000 queries; + C/OpenMP port of dvr.render on all 30000 rays "
-            f"({np.mean([e[2] for e in est]) * 1e3:.0f} ms, {dvr_ref.num_threads()} threads)")
+    parts = {k: float(np.mean([e[2][k] for e in est])) for k in est[0][2]}
+    return (f"per step ({np.mean([e[1] for e in est]):.1f} s of CPU work): MSDA fwd+bwd (torch CPU grid_sample formula = "
+            f"the reference's CPU path) on 1 camera at {CPU_Q_SMALL} and {CPU_Q_LARGE} queries, affine fit -> 6 cams x 40000 "
+            f"queries; LatentRendering core (reference formula, torch CPU) on {CPU_LR_CELLS}/40000 cells, scaled; head ray "
+            f"sampler+CE (reference formula, torch CPU) on {CPU_CE_RAYS}/30000 rays, scaled; C/OpenMP port of dvr.render on "
+            f"all 30000 rays ({dvr_ref.num_threads()} threads).  Full-step estimates (s): "
+            + ", ".join(f"{k}={v:.2f}" for k, v in parts.items()))
 
 
 def cpu_baseline(sample_only=False, steps=2, warmup=1):

@@ -205,6 +205,31 @@ int vidar_ray_argmax(const float* sigma, const float* origin, const float* point
                      const int32_t* frame, float* depth, float* index,
                      int R, int F, int Z, int Y, int X, int num_way, float step, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * (ii-c) LatentRendering core
+ *   (projects/mmdet3d_plugin/bevformer/modules/ray_operations/latent_rendering.py:98-161:
+ *   everything between the three Linear layers).  act: 0 = 'exp' (1-exp(-relu x)), 1 = 'sigmoid'.
+ *   CHANNEL-LAST maps, as the Linear layers emit them:
+ *   occ    [bs, Hb, Wb, D]     output of unsup_raymarching_head (:94), D = pred_height
+ *   feat   [bs, Hb, Wb, D*G]   output of lora_a (:134); channel = d*G + j
+ *   prob   [bs, Hb, Wb, D]     out: occ_path_prob (:127-128)
+ *   pooled [bs, Hb*Wb, D*G]    out: ray-pooled feature that feeds lora_b (:148-153)
+ *   grid_num waypoints of step grid_step / (min(Hb,Wb)//2) (:101-104); eps (:80,147).
+ *   Supported: D a power of two <= 32, G in {1, 2, 4}.
+ * ---------------------------------------------------------------------------------- */
+int vidar_latent_render_forward(const float* occ, const float* feat, float* prob, float* pooled,
+                                int bs, int D, int G, int Hb, int Wb, int grid_num,
+                                float grid_step, float eps, int act, void* stream);
+
+/* Backward.  grad_prob [bs,Hb,Wb,D] = gradient reaching `prob` from outside the core (the
+ * final product, :158-160); grad_pooled [bs,Hb*Wb,D*G].  grad_prob_total [bs,Hb,Wb,D] is
+ * scratch (fully overwritten).  grad_occ, grad_feat: caller-zeroed, shaped like occ, feat. */
+int vidar_latent_render_backward(const float* occ, const float* feat, const float* prob,
+                                 const float* grad_prob, const float* grad_pooled,
+                                 float* grad_prob_total, float* grad_occ, float* grad_feat,
+                                 int bs, int D, int G, int Hb, int Wb, int grid_num,
+                                 float grid_step, float eps, int act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,45 @@
+"""LatentRendering: CPU oracle + module host logic against goldens from the REFERENCE class
+(tools/make_golden_latent.py).  The CUDA core is replaced by the oracle core here."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import latent_render_ref as ref
+from tests import latent_cases as lc
+from vidar_b200.modules import latent_rendering as lr
+from vidar_b200.registry import build_attention
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "latent_rendering.npz")
+
+
+@pytest.fixture()
+def oracle_core(monkeypatch):
+    def core(occ, feat, grid_num, grid_step, eps, act):
+        return ref.latent_core(occ, feat, grid_num, grid_step, eps, "sigmoid" if act == 1 else "exp")
+    monkeypatch.setattr(lr, "latent_render_core", core)
+
+
+@pytest.mark.parametrize("tag,cfg,seed", [("sig", lc.CFG, 20), ("exp", lc.CFG_EXP, 21)])
+def test_module_with_oracle_core_matches_reference_class(oracle_core, tag, cfg, seed):
+    g = np.load(GOLD)
+    m = build_attention(cfg)
+    assert sorted(m.state_dict().keys()) == list(g[f"{tag}_params"])
+    m.load_state_dict(lc.seeded_state(m, seed))
+    c = lc.case()
+    e = c["embed"].clone().requires_grad_(True)
+    out = m(e)
+    out.backward(c["grad"])
+    np.testing.assert_allclose(out.detach().numpy(), g[f"{tag}_out"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(e.grad.numpy(), g[f"{tag}_gembed"], rtol=1e-3, atol=1e-6)
+    for n, p in m.named_parameters():
+        key = f"{tag}_g_{n}"
+        if key in g:
+            np.testing.assert_allclose(p.grad.numpy(), g[key], rtol=1e-3, atol=1e-6)
+
+
+def test_no_cpu_fallback():
+    m = build_attention(lc.CFG)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        m(lc.case()["embed"])

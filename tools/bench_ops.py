@@ -98,6 +98,31 @@ def main():
         out["ray_ce_30k_rays_512wp_fwd_bwd_ms"]["torch_eager_reference_formula"] = f"failed: {e}"
     finally:
         torch.set_default_device("cpu")
+    # ---- LatentRendering core: 200x200 BEV, 16 heights, 256 waypoints
+    from oracle import latent_render_ref
+    from vidar_b200.modules.latent_rendering import latent_render_core
+    g2 = torch.Generator(device=dev).manual_seed(1)
+    occ = torch.randn(1, 200, 200, 16, device=dev, generator=g2)
+    feat = torch.randn(1, 200, 200, 16, device=dev, generator=g2)
+
+    def lr_ours():
+        o, f = occ.detach().requires_grad_(True), feat.detach().requires_grad_(True)
+        p, q = latent_render_core(o, f, 256, 0.5, 1e-3, 1)
+        (p.sum() + q.sum()).backward()
+
+    def lr_eager():
+        o, f = occ.detach().requires_grad_(True), feat.detach().requires_grad_(True)
+        p, q = latent_render_ref.latent_core(o, f, 256, 0.5, 1e-3, "sigmoid")
+        (p.sum() + q.sum()).backward()
+
+    out["latent_render_core_200x200x16_256wp_fwd_bwd_ms"] = {"vidar_b200": timed(lr_ours)}
+    try:
+        torch.set_default_device(dev)
+        out["latent_render_core_200x200x16_256wp_fwd_bwd_ms"]["torch_eager_reference_formula"] = timed(lr_eager, n=3, warm=1)
+    except Exception as e:
+        out["latent_render_core_200x200x16_256wp_fwd_bwd_ms"]["torch_eager_reference_formula"] = f"failed: {e}"
+    finally:
+        torch.set_default_device("cpu")
     print(json.dumps(out, indent=1))
 
 
