@@ -295,36 +295,62 @@ def run_ours(args):
     h2d = sum(t.numel() * 4 for h in host_in for t in h.values()) + 4 * (
         h_sigma.numel() + h_origin.numel() + h_points.numel() + h_tindex.numel()
         + h_embed.numel() + h_gembed.numel())
-    host_out = None
+    # Copies and compute are pipelined on three streams (H2D / compute / D2H): while camera c
+    # computes, camera c+1 is uploading and camera c-1 is downloading (PCIe is full duplex).
+    # A step still ends with every result in pinned host memory.
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    s_cmp = torch.cuda.current_stream(dev)
+
+    def upload(host_tensors):
+        with torch.cuda.stream(s_in):
+            t = [h.to(dev, non_blocking=True) for h in host_tensors]
+            ev_ = torch.cuda.Event()
+            ev_.record(s_in)
+        return t, ev_
+
+    def download(dev_tensors, key):
+        nonlocal host_out
+        if key not in host_out:
+            host_out[key] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in dev_tensors]
+        done = torch.cuda.Event()
+        done.record(s_cmp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            for hb, t in zip(host_out[key], dev_tensors):
+                hb.copy_(t, non_blocking=True)
+                t.record_stream(s_out)
+
+    host_out = {}
 
     def e2e_step():
-        nonlocal host_out
-        d_out = []
-        for h, s in zip(host_in, seg_in):
-            v = h["value"].to(dev, non_blocking=True).requires_grad_(True)
-            loc = h["loc"].to(dev, non_blocking=True).requires_grad_(True)
-            aw = h["attn"].to(dev, non_blocking=True).requires_grad_(True)
-            go = h["grad_out"].to(dev, non_blocking=True)
+        ups = [upload([h[k] for k in ("value", "loc", "attn", "grad_out")]) for h in host_in]
+        up_r = upload([h_sigma, h_origin, h_points, h_tindex])
+        up_l = upload([h_embed, h_gembed])
+        for i, (t, e_) in enumerate(ups):
+            s_cmp.wait_event(e_)
+            for x in t:
+                x.record_stream(s_cmp)
+            v, loc, aw, go = t
+            v.requires_grad_(True), loc.requires_grad_(True), aw.requires_grad_(True)
             out = msda.MultiScaleDeformableAttnFunction_fp32.apply(v, shapes, lsi, loc, aw, 64)
             out.backward(go)
-            d_out += [out.detach(), v.grad, loc.grad, aw.grad]
-        sg = h_sigma.to(dev, non_blocking=True)
-        og = h_origin.to(dev, non_blocking=True)
-        pt = h_points.to(dev, non_blocking=True)
-        ti = h_tindex.to(dev, non_blocking=True)
-        d_out += render.dvr.render(sg, og, pt, ti, "l2")
-        emb = h_embed.to(dev, non_blocking=True).requires_grad_(True)
+            download([out.detach(), v.grad, loc.grad, aw.grad], ("msda", i))
+        (sg, og, pt, ti), e_ = up_r
+        s_cmp.wait_event(e_)
+        for x in (sg, og, pt, ti):
+            x.record_stream(s_cmp)
+        (emb, gemb), e_ = up_l
+        s_cmp.wait_event(e_)
+        emb.record_stream(s_cmp), gemb.record_stream(s_cmp)
+        emb.requires_grad_(True)
         lo = latent(emb)
-        lo.backward(h_gembed.to(dev, non_blocking=True))
+        lo.backward(gemb)
+        download([lo.detach(), emb.grad], "latent")
         sg2 = sg[0].detach().requires_grad_(True)
         ce, valid = ray_head.ray_ce(sg2, og[0].contiguous(), pt[0].contiguous(), ti[0].to(torch.int32), WAYPOINTS, 1.0)
         ce.sum().backward()
-        d_out += [lo.detach(), emb.grad, ce.detach(), sg2.grad]
-        if host_out is None:
-            host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in d_out]
-        for hbuf, t in zip(host_out, d_out):
-            hbuf.copy_(t, non_blocking=True)
-        return d_out
+        download([ce.detach(), sg2.grad] + list(render.dvr.render(sg, og, pt, ti, "l2")), "rays")
+        s_cmp.wait_stream(s_out)        # the step's results are on the host before it ends
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -341,11 +367,11 @@ def run_ours(args):
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    d2h = sum(t.numel() * 4 for t in host_out)
+    d2h = sum(t.numel() * 4 for ts in host_out.values() for t in ts)
     e2e = {"value": RAYS / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "api": "MultiScaleDeformableAttnFunction_fp32.apply+backward, LatentRendering module, ray_head.ray_ce, "
-                  "dvr.render; pinned host tensors in, pinned host tensors out"}
+                  "dvr.render; pinned host tensors in, pinned host tensors out; H2D / compute / D2H on three streams"}
 
     if rank != 0:
         if world > 1:
