@@ -230,6 +230,27 @@ int vidar_latent_render_backward(const float* occ, const float* feat, const floa
                                  int bs, int D, int G, int Hb, int Wb, int grid_num,
                                  float grid_step, float eps, int act, void* stream);
 
+/* The same four kernels, one phase per call, on a range [cell0, cell0+ncells) of the
+ * bs*Hb*Wb BEV cells (row-major): when the cells are sharded over GPUs the host places a
+ * collective on the small maps between the phases (vidar_b200/modules/latent_rendering.py).
+ * Outputs are indexed by GLOBAL cell; scatter targets (grad_*) are caller-zeroed full maps
+ * that receive this range's contributions. */
+int vidar_latent_prob_forward(const float* occ, float* prob, int bs, int D, int Hb, int Wb,
+                              int grid_num, float grid_step, int act,
+                              long long cell0, long long ncells, void* stream);
+int vidar_latent_pool_forward(const float* prob, const float* feat, float* pooled,
+                              int bs, int D, int G, int Hb, int Wb, int grid_num,
+                              float grid_step, float eps,
+                              long long cell0, long long ncells, void* stream);
+int vidar_latent_pool_backward(const float* prob, const float* feat, const float* grad_pooled,
+                               float* grad_prob_map, float* grad_feat,
+                               int bs, int D, int G, int Hb, int Wb, int grid_num,
+                               float grid_step, float eps,
+                               long long cell0, long long ncells, void* stream);
+int vidar_latent_prob_backward(const float* occ, const float* grad_prob_total, float* grad_occ,
+                               int bs, int D, int Hb, int Wb, int grid_num, float grid_step,
+                               int act, long long cell0, long long ncells, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

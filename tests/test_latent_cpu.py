@@ -16,7 +16,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "latent_rendering.npz")
 
 @pytest.fixture()
 def oracle_core(monkeypatch):
-    def core(occ, feat, grid_num, grid_step, eps, act):
+    def core(occ, feat, grid_num, grid_step, eps, act, group=None):
         return ref.latent_core(occ, feat, grid_num, grid_step, eps, "sigmoid" if act == 1 else "exp")
     monkeypatch.setattr(lr, "latent_render_core", core)
 

@@ -35,6 +35,7 @@ namespace {
 struct LrDims {
   int bs, D, G, Hb, Wb, grid_num, act;   // G = feature channels per height
   float tstep, eps;
+  long long cell0, ncells;               // this call handles cells [cell0, cell0 + ncells) of bs*Hb*Wb
 };
 
 struct Bil {
@@ -157,9 +158,10 @@ constexpr int kCellsPerBlock = 8;
   const int WPI = 32 / LPW;                  /* waypoints per iteration */          \
   const int lane = threadIdx.x & 31;                                                 \
   const int slot = lane / LPW, ch = (lane % LPW) * VEC;                             \
-  const long long cell = (long long)blockIdx.x * kCellsPerBlock + (threadIdx.x >> 5); \
+  const long long cidx = (long long)blockIdx.x * kCellsPerBlock + (threadIdx.x >> 5); \
   const int HW = L.Hb * L.Wb;                                                        \
-  if (cell >= (long long)L.bs * HW) return;                                          \
+  if (cidx >= L.ncells) return;                                                      \
+  const long long cell = L.cell0 + cidx;                                             \
   const int b = (int)(cell / HW), u = (int)(cell % HW);                             \
   const Cell c = cell_geometry(L, u / L.Wb, u % L.Wb);
 
@@ -412,7 +414,7 @@ latent_pool_bwd_kernel(LrDims L, const float* __restrict__ prob, const float* __
 }
 
 int check_lr(LrDims& L, int bs, int D, int G, int Hb, int Wb, int grid_num, float grid_step, float eps,
-             int act, int& vec, const char* who) {
+             int act, int& vec, const char* who, long long cell0 = 0, long long ncells = -1) {
   VIDAR_REQUIRE(bs > 0 && D > 0 && G > 0 && Hb > 1 && Wb > 1 && grid_num > 0,
                 "%s: bad sizes bs=%d D=%d G=%d Hb=%d Wb=%d grid_num=%d", who, bs, D, G, Hb, Wb, grid_num);
   VIDAR_REQUIRE(act == 0 || act == 1, "Only support exp or sigmoid activation_fn for now.");
@@ -422,13 +424,16 @@ int check_lr(LrDims& L, int bs, int D, int G, int Hb, int Wb, int grid_num, floa
   VIDAR_REQUIRE((long long)Hb * Wb * D * G < (1LL << 31), "%s: BEV map too large", who);
   vec = (D % 4 == 0) ? 4 : 1;
   const int half = (Hb < Wb ? Hb : Wb) / 2;
-  L = LrDims{bs, D, G, Hb, Wb, grid_num, act, (float)((double)grid_step / (double)half), eps};
+  const long long total = (long long)bs * Hb * Wb;
+  if (ncells < 0) ncells = total - cell0;
+  VIDAR_REQUIRE(cell0 >= 0 && ncells >= 0 && cell0 + ncells <= total, "%s: bad cell range [%lld, +%lld) of %lld",
+                who, cell0, ncells, total);
+  L = LrDims{bs, D, G, Hb, Wb, grid_num, act, (float)((double)grid_step / (double)half), eps, cell0, ncells};
   return VIDAR_OK;
 }
 
 inline unsigned lr_blocks(const LrDims& L) {
-  const long long cells = (long long)L.bs * L.Hb * L.Wb;
-  return (unsigned)((cells + kCellsPerBlock - 1) / kCellsPerBlock);
+  return (unsigned)((L.ncells + kCellsPerBlock - 1) / kCellsPerBlock);
 }
 
 }  // namespace
@@ -494,4 +499,65 @@ extern "C" int vidar_latent_render_backward(const float* occ, const float* feat,
   if (vec == 4) latent_prob_bwd_kernel<4><<<grid, block, 0, st>>>(L, occ, grad_prob_total, grad_occ);
   else latent_prob_bwd_kernel<1><<<grid, block, 0, st>>>(L, occ, grad_prob_total, grad_occ);
   return check_launch("LatentRendering.backward(prob)");
+}
+
+// ---- phase-wise entry points on a cell range: lets the host put a collective between the
+// phases when the BEV cells are sharded over GPUs.
+extern "C" int vidar_latent_prob_forward(const float* occ, float* prob, int bs, int D, int Hb, int Wb,
+                                         int grid_num, float grid_step, int act, long long cell0,
+                                         long long ncells, void* stream) {
+  LrDims L;
+  int vec;
+  int rc = check_lr(L, bs, D, 1, Hb, Wb, grid_num, grid_step, 0.f, act, vec, "LatentRendering.prob_forward", cell0, ncells);
+  if (rc) return rc;
+  VIDAR_REQUIRE(occ && prob, "LatentRendering.prob_forward: null pointer argument");
+  if (L.ncells == 0) return VIDAR_OK;
+  const dim3 grid(lr_blocks(L)), block(kCellsPerBlock * 32);
+  if (vec == 4) latent_prob_fwd_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>(L, occ, prob);
+  else latent_prob_fwd_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(L, occ, prob);
+  return check_launch("LatentRendering.prob_forward");
+}
+
+extern "C" int vidar_latent_pool_forward(const float* prob, const float* feat, float* pooled, int bs, int D,
+                                         int G, int Hb, int Wb, int grid_num, float grid_step, float eps,
+                                         long long cell0, long long ncells, void* stream) {
+  LrDims L;
+  int vec;
+  int rc = check_lr(L, bs, D, G, Hb, Wb, grid_num, grid_step, eps, 1, vec, "LatentRendering.pool_forward", cell0, ncells);
+  if (rc) return rc;
+  VIDAR_REQUIRE(prob && feat && pooled, "LatentRendering.pool_forward: null pointer argument");
+  if (L.ncells == 0) return VIDAR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  LR_DISPATCH_VG(latent_pool_fwd_kernel, L, prob, feat, pooled);
+  return check_launch("LatentRendering.pool_forward");
+}
+
+extern "C" int vidar_latent_pool_backward(const float* prob, const float* feat, const float* grad_pooled,
+                                          float* grad_prob_map, float* grad_feat, int bs, int D, int G,
+                                          int Hb, int Wb, int grid_num, float grid_step, float eps,
+                                          long long cell0, long long ncells, void* stream) {
+  LrDims L;
+  int vec;
+  int rc = check_lr(L, bs, D, G, Hb, Wb, grid_num, grid_step, eps, 1, vec, "LatentRendering.pool_backward", cell0, ncells);
+  if (rc) return rc;
+  VIDAR_REQUIRE(prob && feat && grad_pooled && grad_prob_map && grad_feat, "LatentRendering.pool_backward: null pointer argument");
+  if (L.ncells == 0) return VIDAR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  LR_DISPATCH_VG(latent_pool_bwd_kernel, L, prob, feat, grad_pooled, grad_prob_map, grad_feat);
+  return check_launch("LatentRendering.pool_backward");
+}
+
+extern "C" int vidar_latent_prob_backward(const float* occ, const float* grad_prob_total, float* grad_occ,
+                                          int bs, int D, int Hb, int Wb, int grid_num, float grid_step,
+                                          int act, long long cell0, long long ncells, void* stream) {
+  LrDims L;
+  int vec;
+  int rc = check_lr(L, bs, D, 1, Hb, Wb, grid_num, grid_step, 0.f, act, vec, "LatentRendering.prob_backward", cell0, ncells);
+  if (rc) return rc;
+  VIDAR_REQUIRE(occ && grad_prob_total && grad_occ, "LatentRendering.prob_backward: null pointer argument");
+  if (L.ncells == 0) return VIDAR_OK;
+  const dim3 grid(lr_blocks(L)), block(kCellsPerBlock * 32);
+  if (vec == 4) latent_prob_bwd_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>(L, occ, grad_prob_total, grad_occ);
+  else latent_prob_bwd_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(L, occ, grad_prob_total, grad_occ);
+  return check_launch("LatentRendering.prob_backward");
 }

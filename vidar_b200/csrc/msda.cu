@@ -70,18 +70,45 @@ __device__ __forceinline__ void decode_sample(float lx, float ly, int Hl, int Wl
   }
 }
 
+// Blackwell packed fp32: one FFMA2 does two fused multiply-adds (fma.rn.f32x2, sm_100+), so
+// a float4 of channels costs two issue slots instead of four.  Same IEEE rounding as FFMA.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4_fma(float4& a, float s, const float4& v) {
-  a.x = fmaf(s, v.x, a.x);
-  a.y = fmaf(s, v.y, a.y);
-  a.z = fmaf(s, v.z, a.z);
-  a.w = fmaf(s, v.w, a.w);
+  const u64 ss = pk(s, s);
+  unpk(ffma2(ss, pk(v.x, v.y), pk(a.x, a.y)), a.x, a.y);
+  unpk(ffma2(ss, pk(v.z, v.w), pk(a.z, a.w)), a.z, a.w);
 }
 __device__ __forceinline__ float f4_dot(const float4& a, const float4& b) {
-  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+  float lo, hi;
+  unpk(ffma2(pk(a.x, a.y), pk(b.x, b.y), fmul2(pk(a.z, a.w), pk(b.z, b.w))), lo, hi);
+  return lo + hi;
 }
 __device__ __forceinline__ float4 f4_scale(float s, const float4& v) {
-  return make_float4(s * v.x, s * v.y, s * v.z, s * v.w);
+  float4 r;
+  const u64 ss = pk(s, s);
+  unpk(fmul2(ss, pk(v.x, v.y)), r.x, r.y);
+  unpk(fmul2(ss, pk(v.z, v.w)), r.z, r.w);
+  return r;
 }
 
 // Which (b,q,h) items does this warp own?  Returns false if none.

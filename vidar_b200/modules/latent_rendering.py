@@ -60,7 +60,84 @@ class _LatentRenderCore(torch.autograd.Function):
         return grad_occ, grad_feat, None, None, None, None
 
 
-latent_render_core = _LatentRenderCore.apply
+class _ShardedLatentRenderCore(torch.autograd.Function):
+    """Same op with the BEV cells sharded over the ranks of `group`.  Inputs and
+    outputs are replicated; each rank marches only its contiguous share of the cells and the
+    2.56 MB maps are all-reduced between the phases:
+      forward : prob(local cells) -> all_reduce(prob) -> pooled(local cells) -> all_reduce(pooled)
+      backward: pool-bwd(local) -> all_reduce(grad_prob_map, grad_feat) -> prob-bwd(local)
+                -> all_reduce(grad_occ).
+    Upstream gradients must be replicated (they are: everything after this op is)."""
+
+    @staticmethod
+    def _range(n, group):
+        import torch.distributed as dist
+        from ..sharding import shard_range
+        lo, hi = shard_range(n, dist.get_rank(group), dist.get_world_size(group))
+        return lo, hi - lo
+
+    @staticmethod
+    def forward(ctx, occ, feat, grid_num, grid_step, eps, act, group):
+        import torch.distributed as dist
+        _lib.require_cuda(occ=occ.contiguous(), feat=feat.contiguous())
+        occ, feat = occ.float().contiguous(), feat.float().contiguous()
+        bs, Hb, Wb, D = occ.shape
+        Ca = feat.shape[-1]
+        c0, n = _ShardedLatentRenderCore._range(bs * Hb * Wb, group)
+        prob = torch.zeros_like(occ)
+        pooled = torch.zeros((bs, Hb * Wb, Ca), dtype=torch.float32, device=occ.device)
+        L = _lib.lib()
+        with torch.cuda.device(occ.device):
+            st = _lib.stream_ptr(occ.device)
+            _lib.check(L.vidar_latent_prob_forward(_lib.ptr(occ), _lib.ptr(prob), bs, D, Hb, Wb, int(grid_num),
+                                                   float(grid_step), int(act), c0, n, st))
+            dist.all_reduce(prob, group=group)
+            _lib.check(L.vidar_latent_pool_forward(_lib.ptr(prob), _lib.ptr(feat), _lib.ptr(pooled), bs, D, Ca // D,
+                                                   Hb, Wb, int(grid_num), float(grid_step), float(eps), c0, n, st))
+            dist.all_reduce(pooled, group=group)
+        ctx.save_for_backward(occ, feat, prob)
+        ctx.cfg = (int(grid_num), float(grid_step), float(eps), int(act), group, c0, n)
+        return prob, pooled
+
+    @staticmethod
+    def backward(ctx, grad_prob, grad_pooled):
+        import torch.distributed as dist
+        occ, feat, prob = ctx.saved_tensors
+        grid_num, grid_step, eps, act, group, c0, n = ctx.cfg
+        bs, Hb, Wb, D = occ.shape
+        Ca = feat.shape[-1]
+        grad_pooled = grad_pooled.float().contiguous()
+        # one buffer [2, ...] so the two partial maps travel in a single all-reduce
+        both = torch.zeros((2,) + tuple(occ.shape), dtype=torch.float32, device=occ.device) if Ca == D else None
+        gpm = both[0] if both is not None else torch.zeros_like(occ)
+        gfe = both[1] if both is not None else torch.zeros_like(feat)
+        grad_occ = torch.zeros_like(occ)
+        L = _lib.lib()
+        with torch.cuda.device(occ.device):
+            st = _lib.stream_ptr(occ.device)
+            _lib.check(L.vidar_latent_pool_backward(_lib.ptr(prob), _lib.ptr(feat), _lib.ptr(grad_pooled), _lib.ptr(gpm),
+                                                    _lib.ptr(gfe), bs, D, Ca // D, Hb, Wb, grid_num, grid_step, eps,
+                                                    c0, n, st))
+            if both is not None:
+                dist.all_reduce(both, group=group)
+            else:
+                dist.all_reduce(gpm, group=group)
+                dist.all_reduce(gfe, group=group)
+            total = (gpm + grad_prob.float()).contiguous()
+            _lib.check(L.vidar_latent_prob_backward(_lib.ptr(occ), _lib.ptr(total), _lib.ptr(grad_occ), bs, D, Hb, Wb,
+                                                    grid_num, grid_step, act, c0, n, st))
+            dist.all_reduce(grad_occ, group=group)
+        return grad_occ, gfe.clone() if both is not None else gfe, None, None, None, None, None
+
+
+def latent_render_core(occ, feat, grid_num, grid_step, eps, act, group=None):
+    """(occ, feat) -> (prob, pooled).  `group`: a torch.distributed process group over which the BEV
+    cells are sharded (None or a 1-rank group = single GPU)."""
+    if group is not None:
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            return _ShardedLatentRenderCore.apply(occ, feat, grid_num, grid_step, eps, act, group)
+    return _LatentRenderCore.apply(occ, feat, grid_num, grid_step, eps, act)
 
 
 @ATTENTION.register_module()
@@ -86,6 +163,7 @@ class LatentRendering(BaseModule):
         self.pred_height = pred_height
         self.lora_a = nn.Linear(self.embed_dims, self.embed_dims // reduction)
         self.lora_b = nn.Linear(self.embed_dims // reduction, self.embed_dims)
+        self.process_group = None     # set to a process group to shard the BEV cells over its ranks
 
     def forward(self, embed, eps=1e-3, **kwargs):
         """embed [bs, bev_h, bev_w, embed_dims] -> same shape."""
@@ -94,7 +172,8 @@ class LatentRendering(BaseModule):
         bs, bev_h, bev_w, _ = embed.shape
         occ = self.unsup_raymarching_head(embed)            # [bs, h, w, pred_height]   (:94)
         feat = self.lora_a(embed)                           # [bs, h, w, embed/reduction] (:134)
-        prob, pooled = latent_render_core(occ, feat, self.grid_num, self.grid_step, eps, _ACT[self.act])
+        prob, pooled = latent_render_core(occ, feat, self.grid_num, self.grid_step, eps, _ACT[self.act],
+                                          self.process_group)
         out = self.lora_b(pooled).view(bs, bev_h, bev_w, self.embed_dims)       # (:153-155)
         out = out.view(bs, bev_h, bev_w, self.pred_height, -1) * prob.view(bs, bev_h, bev_w, self.pred_height, 1)
         return out.view(bs, bev_h, bev_w, self.embed_dims)
