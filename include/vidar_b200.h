@@ -251,6 +251,17 @@ int vidar_latent_prob_backward(const float* occ, const float* grad_prob_total, f
                                int bs, int D, int Hb, int Wb, int grid_num, float grid_step,
                                int act, long long cell0, long long ncells, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * (i-b) BEV pillar -> camera projection, BEVFormerEncoder.point_sampling
+ *   (projects/mmdet3d_plugin/bevformer/modules/encoder.py:94-156)
+ *   ref3d [B, D, Q, 3] normalised pillar points; lidar2img [B, cams, 4, 4];
+ *   pc_range_host: 6 floats in HOST memory (x0,y0,z0,x1,y1,z1); img_h/img_w = img_shape
+ *   out: ref_cam [cams, B, Q, D, 2], bev_mask [cams, B, Q, D] (uint8 0/1).
+ * ---------------------------------------------------------------------------------- */
+int vidar_point_sampling(const float* ref3d, const float* lidar2img, const float* pc_range_host,
+                         float* ref_cam, unsigned char* bev_mask, int B, int D, int Q, int cams,
+                         float img_h, float img_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
