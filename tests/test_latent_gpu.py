@@ -9,6 +9,7 @@ import torch
 from oracle import latent_render_ref as ref
 from tests import latent_cases as lc
 from vidar_b200.modules.latent_rendering import latent_render_core
+import vidar_b200.modules  # noqa: F401  (registers the classes)
 from vidar_b200.registry import build_attention
 
 pytestmark = pytest.mark.gpu

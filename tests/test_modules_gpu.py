@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from tests import module_cases as mc
+import vidar_b200.modules  # noqa: F401  (registers the classes)
 from vidar_b200.registry import build_attention
 
 pytestmark = pytest.mark.gpu

@@ -363,6 +363,174 @@ msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
   }
 }
 
+// ---- small L*P (temporal self-attention, future decoder: L*P = 4 or 8) -------------------
+// When a 32-sample chunk holds at least NG whole items, give each group of CV lanes its OWN
+// item: the group walks that item's L*P samples and finishes the head vector by itself, so the
+// cross-group shuffle reduction + flush of the generic MULTI path (8 shuffles per item, i.e.
+// 2 shuffles per sample at L*P = 4) disappears and every group stores 128 contiguous bytes.
+template <int CV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+msda_forward_small_kernel(const MsdaParams p, float* __restrict__ out) {
+  constexpr int NG = 32 / CV;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / CV, cl = lane % CV;
+  long long item0;
+  if (!warp_items(p, item0)) return;
+  const float* loc0 = p.loc + (size_t)item0 * p.LP * 2;
+  const float* att0 = p.attn + (size_t)item0 * p.LP;
+  const unsigned pix = (unsigned)p.pix_stride;
+  // lane j decodes sample j of the chunk (32 samples = ipw items)
+  int base = 0, meta = 0;
+  float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
+  if (item0 + (lane >> p.lp_shift) < p.items) {
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc0) + lane);
+    const float aw = __ldg(att0 + lane);
+    const int l = (lane & (p.LP - 1)) / p.P;
+    const int Hl = (int)__ldg(p.shapes + 2 * l), Wl = (int)__ldg(p.shapes + 2 * l + 1);
+    float lh, lw;
+    decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw, p.pix_stride);
+    const float hh = 1.f - lh, hw = 1.f - lw;
+    w1 = (meta & 1) ? aw * (hh * hw) : 0.f;
+    w2 = (meta & 2) ? aw * (hh * lw) : 0.f;
+    w3 = (meta & 4) ? aw * (lh * hw) : 0.f;
+    w4 = (meta & 8) ? aw * (lh * lw) : 0.f;
+  }
+  const int rounds = p.ipw / NG;
+  for (int r = 0; r < rounds; ++r) {
+    const int il = r * NG + g;                       // this group's item in the chunk
+    const long long item = item0 + il;
+    const bool live = item < p.items;
+    const float* vb = p.value + (live ? slab_offset(p, item) : 0) + cl * 4;
+    asm volatile("" : "+l"(vb));
+    float4 acc = f4_zero();
+    for (int sidx = 0; sidx < p.LP; ++sidx) {
+      const int src = (il << p.lp_shift) + sidx;
+      const int sbase = __shfl_sync(0xffffffffu, base, src);
+      const int smeta = __shfl_sync(0xffffffffu, meta, src);
+      const float a1 = __shfl_sync(0xffffffffu, w1, src);
+      const float a2 = __shfl_sync(0xffffffffu, w2, src);
+      const float a3 = __shfl_sync(0xffffffffu, w3, src);
+      const float a4 = __shfl_sync(0xffffffffu, w4, src);
+      if (smeta & 15) {
+        const unsigned o1 = (unsigned)sbase;
+        const unsigned o2 = o1 + ((smeta & 16) ? pix : 0u);
+        const unsigned o3 = o1 + (unsigned)(smeta >> 5);
+        const unsigned o4 = o3 + (o2 - o1);
+        const float4 v1 = ldg4(vb + o1);
+        const float4 v2 = ldg4(vb + o2);
+        const float4 v3 = ldg4(vb + o3);
+        const float4 v4 = ldg4(vb + o4);
+        f4_fma(acc, a1, v1);
+        f4_fma(acc, a2, v2);
+        f4_fma(acc, a3, v3);
+        f4_fma(acc, a4, v4);
+      }
+    }
+    if (live) *reinterpret_cast<float4*>(out + (size_t)item * p.C + cl * 4) = acc;
+  }
+}
+
+template <int CV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+msda_backward_small_kernel(const MsdaParams p, const float* __restrict__ grad_out,
+                           float* __restrict__ grad_value, float* __restrict__ grad_loc,
+                           float* __restrict__ grad_attn) {
+  constexpr int NG = 32 / CV;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / CV, cl = lane % CV;
+  long long item0;
+  if (!warp_items(p, item0)) return;
+  const float* loc0 = p.loc + (size_t)item0 * p.LP * 2;
+  const float* att0 = p.attn + (size_t)item0 * p.LP;
+  const unsigned pix = (unsigned)p.pix_stride;
+  int base = 0, meta = 0;
+  float lh = 0.f, lw = 0.f, aw = 0.f, fH = 0.f, fW = 0.f;
+  float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
+  const bool mine = item0 + (lane >> p.lp_shift) < p.items;
+  if (mine) {
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc0) + lane);
+    aw = __ldg(att0 + lane);
+    const int l = (lane & (p.LP - 1)) / p.P;
+    const int Hl = (int)__ldg(p.shapes + 2 * l), Wl = (int)__ldg(p.shapes + 2 * l + 1);
+    decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw, p.pix_stride);
+    fH = (float)Hl;
+    fW = (float)Wl;
+    const float hh = 1.f - lh, hw = 1.f - lw;
+    w1 = (meta & 1) ? aw * (hh * hw) : 0.f;
+    w2 = (meta & 2) ? aw * (hh * lw) : 0.f;
+    w3 = (meta & 4) ? aw * (lh * hw) : 0.f;
+    w4 = (meta & 8) ? aw * (lh * lw) : 0.f;
+  }
+  float r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;
+  const int rounds = p.ipw / NG;
+  const int my_il = lane >> p.lp_shift;              // item (in the chunk) of the sample this lane decoded
+  for (int r = 0; r < rounds; ++r) {
+    const int il = r * NG + g;
+    const long long item = item0 + il;
+    const bool live = item < p.items;
+    const size_t slab = (live ? slab_offset(p, item) : 0) + cl * 4;
+    const float4 go = live ? ldg4(grad_out + (size_t)item * p.C + cl * 4) : f4_zero();
+    const float* vs = p.value + slab;
+    float* gs = grad_value + slab;
+    asm volatile("" : "+l"(vs), "+l"(gs));
+    for (int sidx = 0; sidx < p.LP; ++sidx) {
+      const int src = (il << p.lp_shift) + sidx;
+      const int sbase = __shfl_sync(0xffffffffu, base, src);
+      const int smeta = __shfl_sync(0xffffffffu, meta, src);
+      const float a1 = __shfl_sync(0xffffffffu, w1, src);
+      const float a2 = __shfl_sync(0xffffffffu, w2, src);
+      const float a3 = __shfl_sync(0xffffffffu, w3, src);
+      const float a4 = __shfl_sync(0xffffffffu, w4, src);
+      float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
+      if (smeta & 15) {
+        const unsigned o1 = (unsigned)sbase;
+        const unsigned o2 = o1 + ((smeta & 16) ? pix : 0u);
+        const unsigned o3 = o1 + (unsigned)(smeta >> 5);
+        const unsigned o4 = o3 + (o2 - o1);
+        const float4 v1 = ldg4(vs + o1);
+        const float4 v2 = ldg4(vs + o2);
+        const float4 v3 = ldg4(vs + o3);
+        const float4 v4 = ldg4(vs + o4);
+        red_add_v4(gs + o1, f4_scale(a1, go));
+        red_add_v4(gs + o2, f4_scale(a2, go));
+        red_add_v4(gs + o3, f4_scale(a3, go));
+        red_add_v4(gs + o4, f4_scale(a4, go));
+        d1 = f4_dot(go, v1); d2 = f4_dot(go, v2); d3 = f4_dot(go, v3); d4 = f4_dot(go, v4);
+      }
+      const bool up1 = (cl & (CV / 2)) != 0;
+      const float e0 = __shfl_xor_sync(0xffffffffu, up1 ? d1 : d3, CV / 2);
+      const float e1 = __shfl_xor_sync(0xffffffffu, up1 ? d2 : d4, CV / 2);
+      const float k0 = (up1 ? d3 : d1) + e0;
+      const float k1 = (up1 ? d4 : d2) + e1;
+      const bool up2 = (cl & (CV / 4)) != 0;
+      const float eb = __shfl_xor_sync(0xffffffffu, up2 ? k0 : k1, CV / 4);
+      float k = (up2 ? k1 : k0) + eb;
+#pragma unroll
+      for (int off = CV / 8; off >= 1; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
+      // hand back to the decoding lane: its sample is processed by group (my_il % NG) in round my_il / NG
+      const int back = (my_il & (NG - 1)) * CV;
+      const float t1 = __shfl_sync(0xffffffffu, k, back);
+      const float t2 = __shfl_sync(0xffffffffu, k, back + CV / 4);
+      const float t3 = __shfl_sync(0xffffffffu, k, back + CV / 2);
+      const float t4 = __shfl_sync(0xffffffffu, k, back + CV / 2 + CV / 4);
+      if ((my_il / NG) == r && (lane & (p.LP - 1)) == sidx) { r1 = t1; r2 = t2; r3 = t3; r4 = t4; }
+    }
+  }
+  if (mine) {
+    const float hh = 1.f - lh, hw = 1.f - lw;
+    if (!(meta & 1)) r1 = 0.f;
+    if (!(meta & 2)) r2 = 0.f;
+    if (!(meta & 4)) r3 = 0.f;
+    if (!(meta & 8)) r4 = 0.f;
+    const bool ok = (meta & 15) != 0;
+    const float ga = ok ? (hh * hw) * r1 + (hh * lw) * r2 + (lh * hw) * r3 + (lh * lw) * r4 : 0.f;
+    const float gx = ok ? fW * aw * (hh * (r2 - r1) + lh * (r4 - r3)) : 0.f;
+    const float gy = ok ? fH * aw * (hw * (r3 - r1) + lw * (r4 - r2)) : 0.f;
+    grad_attn[(size_t)item0 * p.LP + lane] = ga;
+    reinterpret_cast<float2*>(grad_loc)[(size_t)item0 * p.LP + lane] = make_float2(gx, gy);
+  }
+}
+
 // ---- generic fallback (any C): one thread per (item, channel); scalar atomics.
 __global__ void msda_forward_generic_kernel(const MsdaParams p, float* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -509,8 +677,9 @@ extern "C" int vidar_msda_forward(const float* value, const int64_t* spatial_sha
     const long long nb = num_blocks(p);
     VIDAR_REQUIRE(nb < 2147483647LL, "ms_deform_attn_forward: problem too large");
     const dim3 grid((unsigned)nb), block(kWarpsPerBlock * 32);
-#define VIDAR_FWD(CVV)                                                            \
-  if (p.ipw > 1) msda_forward_kernel<CVV, true><<<grid, block, 0, st>>>(p, out);  \
+#define VIDAR_FWD(CVV)                                                                     \
+  if (p.ipw >= 32 / CVV) msda_forward_small_kernel<CVV><<<grid, block, 0, st>>>(p, out);  \
+  else if (p.ipw > 1) msda_forward_kernel<CVV, true><<<grid, block, 0, st>>>(p, out);     \
   else msda_forward_kernel<CVV, false><<<grid, block, 0, st>>>(p, out)
     if (CV == 8) { VIDAR_FWD(8); }
     else if (CV == 4) { VIDAR_FWD(4); }
@@ -545,7 +714,10 @@ extern "C" int vidar_msda_backward(const float* value, const int64_t* spatial_sh
     VIDAR_REQUIRE(nb < 2147483647LL, "ms_deform_attn_backward: problem too large");
     const dim3 grid((unsigned)nb), block(kWarpsPerBlock * 32);
 #define VIDAR_BWD(CVV)                                                                        \
-  if (p.ipw > 1)                                                                              \
+  if (p.ipw >= 32 / CVV)                                                                      \
+    msda_backward_small_kernel<CVV><<<grid, block, 0, st>>>(p, grad_out, grad_value,         \
+                                                            grad_sampling_loc, grad_attn_weight); \
+  else if (p.ipw > 1)                                                                         \
     msda_backward_kernel<CVV, true><<<grid, block, 0, st>>>(p, grad_out, grad_value,          \
                                                             grad_sampling_loc, grad_attn_weight); \
   else                                                                                        \
