@@ -215,7 +215,8 @@ int vidar_ray_argmax(const float* sigma, const float* origin, const float* point
  *   prob   [bs, Hb, Wb, D]     out: occ_path_prob (:127-128)
  *   pooled [bs, Hb*Wb, D*G]    out: ray-pooled feature that feeds lora_b (:148-153)
  *   grid_num waypoints of step grid_step / (min(Hb,Wb)//2) (:101-104); eps (:80,147).
- *   Supported: D a power of two <= 32, G in {1, 2, 4}.
+ *   Supported: D a power of two <= 32, G in {1, 2, 4, 8, 16} (the reference default
+ *   pred_height=1, reduction=16, embed_dims=256 is D=1, G=16).
  * ---------------------------------------------------------------------------------- */
 int vidar_latent_render_forward(const float* occ, const float* feat, float* prob, float* pooled,
                                 int bs, int D, int G, int Hb, int Wb, int grid_num,
@@ -261,6 +262,24 @@ int vidar_latent_prob_backward(const float* occ, const float* grad_prob_total, f
 int vidar_point_sampling(const float* ref3d, const float* lidar2img, const float* pc_range_host,
                          float* ref_cam, unsigned char* bev_mask, int B, int D, int Q, int cams,
                          float img_h, float img_w, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (iii) nearest neighbour (K = 1) for the Chamfer distance -- SURVEY.md 8(f) item 2
+ *   (third_lib/chamfer_dist/chamferdist/chamferdist/knn.cu:21-260, knn_cpu.cpp:7-106,
+ *   chamfer.py:20-133; used by bevformer/utils/e2e_predictor_utils.py:163-183)
+ *   p1 [N, P1, D], p2 [N, P2, D] (D = 2, 3 or 4); lengths1/2 [N] int64 (NULL = full)
+ *   dists [N, P1] squared distance to the nearest p2 point, idx [N, P1] int64; zero padded
+ *   beyond lengths1.  scratch: N*P1 uint64 (fully overwritten).
+ * ---------------------------------------------------------------------------------- */
+int vidar_nn_forward(const float* p1, const float* p2, const int64_t* lengths1,
+                     const int64_t* lengths2, float* dists, int64_t* idx,
+                     unsigned long long* scratch, int N, int P1, int P2, int D, void* stream);
+
+/* knn_points_backward (knn_cpu.cpp:64-106): grad_p1 [N,P1,D] and grad_p2 [N,P2,D], both
+ * caller-zeroed. */
+int vidar_nn_backward(const float* p1, const float* p2, const int64_t* lengths1,
+                      const int64_t* lengths2, const int64_t* idx, const float* grad_dists,
+                      float* grad_p1, float* grad_p2, int N, int P1, int P2, int D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,30 @@ def _patch(text):
     return text
 
 
+KNN_SRC = "/root/reference/third_lib/chamfer_dist/chamferdist/chamferdist"
+
+
+def build_knn_cpu(force=False):
+    """The reference's CPU KNN (chamferdist ext.cpp + knn_cpu.cpp, built WITHOUT `WITH_CUDA`) compiled
+    unmodified from where it lies -> oracle/_ref/ref_knn_cpu.so.  It runs on any host, so it pins the
+    NN oracle here and can serve as a `kind: "reference"` CPU baseline."""
+    if not os.path.isdir(KNN_SRC):
+        return None
+    out = so_path("ref_knn_cpu")
+    if os.path.exists(out) and not force:
+        return out
+    from torch.utils import cpp_extension
+    os.makedirs(OUT, exist_ok=True)
+    bdir = tempfile.mkdtemp(prefix="ref_knn_build_")
+    try:
+        cpp_extension.load(name="ref_knn_cpu", sources=[os.path.join(KNN_SRC, "ext.cpp"), os.path.join(KNN_SRC, "knn_cpu.cpp")],
+                           extra_include_paths=[KNN_SRC], build_directory=bdir, verbose=False, is_python_module=False)
+        shutil.copy(os.path.join(bdir, "ref_knn_cpu.so"), out)
+    finally:
+        shutil.rmtree(bdir, ignore_errors=True)
+    return out
+
+
 def so_path(name):
     return os.path.join(OUT, name + ".so")
 
@@ -52,6 +76,10 @@ def build(names=None, force=False):
     from torch.utils import cpp_extension
     os.makedirs(OUT, exist_ok=True)
     built = {}
+    if not names or "ref_knn_cpu" in names:
+        k = build_knn_cpu(force)
+        if k:
+            built["ref_knn_cpu"] = k
     for name, (sub, files) in TARGETS.items():
         if names and name not in names:
             continue

@@ -5,6 +5,8 @@ CFG = dict(type="LatentRendering", embed_dims=64, num_pred_fcs=0, pred_height=16
            grid_step=0.5, reduction=4, act="sigmoid")
 CFG_EXP = dict(type="LatentRendering", embed_dims=64, num_pred_fcs=1, pred_height=4, grid_num=40,
                grid_step=0.5, reduction=8, act="exp")      # 8 channels / 4 heights: G = 2
+CFG_D1 = dict(type="LatentRendering", embed_dims=64, num_pred_fcs=0, pred_height=1, grid_num=40,
+              grid_step=0.5, reduction=4, act="sigmoid")    # the class defaults' shape: 1 height, 16 channels
 BEV = (20, 24)
 
 

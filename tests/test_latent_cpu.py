@@ -21,7 +21,7 @@ def oracle_core(monkeypatch):
     monkeypatch.setattr(lr, "latent_render_core", core)
 
 
-@pytest.mark.parametrize("tag,cfg,seed", [("sig", lc.CFG, 20), ("exp", lc.CFG_EXP, 21)])
+@pytest.mark.parametrize("tag,cfg,seed", [("sig", lc.CFG, 20), ("exp", lc.CFG_EXP, 21), ("d1", lc.CFG_D1, 22)])
 def test_module_with_oracle_core_matches_reference_class(oracle_core, tag, cfg, seed):
     g = np.load(GOLD)
     m = build_attention(cfg)

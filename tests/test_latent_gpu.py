@@ -24,7 +24,7 @@ def _close(a, b, what, rtol=1e-4, frac=1e-4):
     assert np.linalg.norm(a - b) <= frac * np.linalg.norm(b) + 1e-30, f"{what}: L2 err {np.linalg.norm(a-b):.3e} vs {np.linalg.norm(b):.3e}"
 
 
-@pytest.mark.parametrize("tag,cfg,seed", [("sig", lc.CFG, 20), ("exp", lc.CFG_EXP, 21)])
+@pytest.mark.parametrize("tag,cfg,seed", [("sig", lc.CFG, 20), ("exp", lc.CFG_EXP, 21), ("d1", lc.CFG_D1, 22)])
 def test_module_on_gpu_matches_reference_class(cuda, tag, cfg, seed):
     g = np.load(GOLD)
     m = build_attention(cfg)

@@ -20,7 +20,7 @@ def main():
     f = mod.get_bev_grids
     mod.get_bev_grids = lambda H, W, bs=1, device="cpu", dtype=torch.float, offset=0.5: f(H, W, bs, "cpu", dtype, offset)
     rec = {}
-    for tag, cfg, seed in (("sig", lc.CFG, 20), ("exp", lc.CFG_EXP, 21)):
+    for tag, cfg, seed in (("sig", lc.CFG, 20), ("exp", lc.CFG_EXP, 21), ("d1", lc.CFG_D1, 22)):
         kw = dict(cfg)
         kw.pop("type")
         m = mod.LatentRendering(**kw)

@@ -420,9 +420,10 @@ int check_lr(LrDims& L, int bs, int D, int G, int Hb, int Wb, int grid_num, floa
   VIDAR_REQUIRE(act == 0 || act == 1, "Only support exp or sigmoid activation_fn for now.");
   VIDAR_REQUIRE((D & (D - 1)) == 0 && D <= 32,
                 "%s: pred_height=%d unsupported (power of two <= 32)", who, D);
-  VIDAR_REQUIRE(G == 1 || G == 2 || G == 4, "%s: %d feature channels per height unsupported (1, 2 or 4)", who, G);
+  VIDAR_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8 || G == 16,
+                "%s: %d feature channels per height unsupported (1, 2, 4, 8 or 16)", who, G);
   VIDAR_REQUIRE((long long)Hb * Wb * D * G < (1LL << 31), "%s: BEV map too large", who);
-  vec = (D % 4 == 0) ? 4 : 1;
+  vec = (D % 4 == 0 && G <= 4) ? 4 : 1;   // a lane keeps VEC*G accumulators in registers
   const int half = (Hb < Wb ? Hb : Wb) / 2;
   const long long total = (long long)bs * Hb * Wb;
   if (ncells < 0) ncells = total - cell0;
@@ -451,7 +452,9 @@ using namespace vidar;
     } else {                                                                           \
       if (G == 1) KERNEL<1, 1><<<grid, block, 0, st>>>(__VA_ARGS__);                   \
       else if (G == 2) KERNEL<1, 2><<<grid, block, 0, st>>>(__VA_ARGS__);              \
-      else KERNEL<1, 4><<<grid, block, 0, st>>>(__VA_ARGS__);                          \
+      else if (G == 4) KERNEL<1, 4><<<grid, block, 0, st>>>(__VA_ARGS__);              \
+      else if (G == 8) KERNEL<1, 8><<<grid, block, 0, st>>>(__VA_ARGS__);              \
+      else KERNEL<1, 16><<<grid, block, 0, st>>>(__VA_ARGS__);                         \
     }                                                                                  \
   } while (0)
 
