@@ -219,38 +219,45 @@ int vidar_ray_argmax(const float* sigma, const float* origin, const float* point
  *   pred_height=1, reduction=16, embed_dims=256 is D=1, G=16).
  * ---------------------------------------------------------------------------------- */
 int vidar_latent_render_forward(const float* occ, const float* feat, float* prob, float* pooled,
-                                int bs, int D, int G, int Hb, int Wb, int grid_num,
+                                float* aux, int bs, int D, int G, int Hb, int Wb, int grid_num,
                                 float grid_step, float eps, int act, void* stream);
 
-/* Backward.  grad_prob [bs,Hb,Wb,D] = gradient reaching `prob` from outside the core (the
- * final product, :158-160); grad_pooled [bs,Hb*Wb,D*G].  grad_prob_total [bs,Hb,Wb,D] is
- * scratch (fully overwritten).  grad_occ, grad_feat: caller-zeroed, shaped like occ, feat. */
+/* aux (may be NULL everywhere): [3, bs, Hb, Wb, D] floats the forward fills (product of the
+ * non-zero transmittance factors, count of zero factors, sum of sampled probabilities) so the
+ * backward does not have to march the rays again to recompute them.
+ *
+ * Backward.  grad_prob [bs,Hb,Wb,D] = gradient reaching `prob` from outside the core (the
+ * final product, :158-160); grad_pooled [bs,Hb*Wb,D*G]; pooled = forward output (needed with aux).
+ * grad_prob_total [bs,Hb,Wb,D] is scratch (fully overwritten).  grad_occ, grad_feat:
+ * caller-zeroed, shaped like occ, feat. */
 int vidar_latent_render_backward(const float* occ, const float* feat, const float* prob,
-                                 const float* grad_prob, const float* grad_pooled,
-                                 float* grad_prob_total, float* grad_occ, float* grad_feat,
-                                 int bs, int D, int G, int Hb, int Wb, int grid_num,
-                                 float grid_step, float eps, int act, void* stream);
+                                 const float* pooled, const float* aux, const float* grad_prob,
+                                 const float* grad_pooled, float* grad_prob_total, float* grad_occ,
+                                 float* grad_feat, int bs, int D, int G, int Hb, int Wb,
+                                 int grid_num, float grid_step, float eps, int act, void* stream);
 
 /* The same four kernels, one phase per call, on a range [cell0, cell0+ncells) of the
  * bs*Hb*Wb BEV cells (row-major): when the cells are sharded over GPUs the host places a
  * collective on the small maps between the phases (vidar_b200/modules/latent_rendering.py).
  * Outputs are indexed by GLOBAL cell; scatter targets (grad_*) are caller-zeroed full maps
  * that receive this range's contributions. */
-int vidar_latent_prob_forward(const float* occ, float* prob, int bs, int D, int Hb, int Wb,
-                              int grid_num, float grid_step, int act,
+int vidar_latent_prob_forward(const float* occ, float* prob, float* aux, int bs, int D, int Hb,
+                              int Wb, int grid_num, float grid_step, int act,
                               long long cell0, long long ncells, void* stream);
-int vidar_latent_pool_forward(const float* prob, const float* feat, float* pooled,
+int vidar_latent_pool_forward(const float* prob, const float* feat, float* pooled, float* aux,
                               int bs, int D, int G, int Hb, int Wb, int grid_num,
                               float grid_step, float eps,
                               long long cell0, long long ncells, void* stream);
-int vidar_latent_pool_backward(const float* prob, const float* feat, const float* grad_pooled,
+int vidar_latent_pool_backward(const float* prob, const float* feat, const float* pooled,
+                               const float* aux, const float* grad_pooled,
                                float* grad_prob_map, float* grad_feat,
                                int bs, int D, int G, int Hb, int Wb, int grid_num,
                                float grid_step, float eps,
                                long long cell0, long long ncells, void* stream);
-int vidar_latent_prob_backward(const float* occ, const float* grad_prob_total, float* grad_occ,
-                               int bs, int D, int Hb, int Wb, int grid_num, float grid_step,
-                               int act, long long cell0, long long ncells, void* stream);
+int vidar_latent_prob_backward(const float* occ, const float* aux, const float* grad_prob_total,
+                               float* grad_occ, int bs, int D, int Hb, int Wb, int grid_num,
+                               float grid_step, int act, long long cell0, long long ncells,
+                               void* stream);
 
 /* ------------------------------------------------------------------------------------
  * (i-b) BEV pillar -> camera projection, BEVFormerEncoder.point_sampling

@@ -168,49 +168,12 @@ constexpr int kCellsPerBlock = 8;
 // ---------------------------------------------------------------- phase 1 forward
 template <int VEC>
 __global__ void __launch_bounds__(kCellsPerBlock * 32)
-latent_prob_fwd_kernel(LrDims L, const float* __restrict__ occ, float* __restrict__ prob) {
+latent_prob_fwd_kernel(LrDims L, const float* __restrict__ occ, float* __restrict__ prob,
+                       float* __restrict__ aux_t, float* __restrict__ aux_nz) {
   LR_PROLOGUE
   const float* omap = occ + (size_t)b * HW * L.D;
-  float acc[VEC];
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) acc[v] = 1.f;
-  const int kend = march_end(L, c.lenG);
-  for (int k0 = 0; k0 < kend; k0 += WPI) {
-    const int k = k0 + slot;
-    if (k < kend) {
-      float gx, gy, len;
-      waypoint(L, c, k, gx, gy, len);
-      if (len < c.lenG) {
-        float x[VEC];
-        sample<VEC>(omap, L.D, ch, bilinear_setup(gx, gy, L.Hb, L.Wb), x);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] *= 1.f - activate(L.act, x[v]);
-      }
-    }
-  }
-#pragma unroll
-  for (int v = 0; v < VEC; ++v)
-    for (int off = LPW; off < 32; off <<= 1) acc[v] *= __shfl_xor_sync(0xffffffffu, acc[v], off);
-  if (slot == 0) {
-    float x[VEC], out[VEC];
-    sample<VEC>(omap, L.D, ch, bilinear_setup(c.cgx, c.cgy, L.Hb, L.Wb), x);
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) out[v] = acc[v] * activate(L.act, x[v]);
-    V<VEC>::st(prob + ((size_t)b * HW + u) * L.D + ch, out);
-  }
-}
-
-// ---------------------------------------------------------------- phase 1 backward
-// grad_prob -> grad_occ.  d prob / d a_k = -a_G * prod_{j != k}(1 - a_j m_j); the product of
-// the others is T / f_k unless a factor is exactly 0 (saturated activation), which is
-// tracked by counting zero factors so nothing is divided by zero.
-template <int VEC>
-__global__ void __launch_bounds__(kCellsPerBlock * 32)
-latent_prob_bwd_kernel(LrDims L, const float* __restrict__ occ, const float* __restrict__ grad_prob,
-                       float* __restrict__ grad_occ) {
-  LR_PROLOGUE
-  const float* omap = occ + (size_t)b * HW * L.D;
-  float* gmap = grad_occ + (size_t)b * HW * L.D;
+  // product of the non-zero factors and the number of exactly-zero ones (saturated activation):
+  // the backward needs "product of the other factors" without dividing by zero
   float tnz[VEC], nz[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { tnz[v] = 1.f; nz[v] = 0.f; }
@@ -237,6 +200,64 @@ latent_prob_bwd_kernel(LrDims L, const float* __restrict__ occ, const float* __r
       tnz[v] *= __shfl_xor_sync(0xffffffffu, tnz[v], off);
       nz[v] += __shfl_xor_sync(0xffffffffu, nz[v], off);
     }
+  if (slot == 0) {
+    float x[VEC], out[VEC];
+    sample<VEC>(omap, L.D, ch, bilinear_setup(c.cgx, c.cgy, L.Hb, L.Wb), x);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) out[v] = (nz[v] > 0.f ? 0.f : tnz[v]) * activate(L.act, x[v]);
+    const size_t o = ((size_t)b * HW + u) * L.D + ch;
+    V<VEC>::st(prob + o, out);
+    if (aux_t) {          // saved for the backward: no second march there
+      V<VEC>::st(aux_t + o, tnz);
+      V<VEC>::st(aux_nz + o, nz);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- phase 1 backward
+// grad_prob -> grad_occ.  d prob / d a_k = -a_G * prod_{j != k}(1 - a_j m_j); the product of
+// the others is T / f_k unless a factor is exactly 0 (saturated activation), which is
+// tracked by counting zero factors so nothing is divided by zero.
+template <int VEC>
+__global__ void __launch_bounds__(kCellsPerBlock * 32)
+latent_prob_bwd_kernel(LrDims L, const float* __restrict__ occ, const float* __restrict__ grad_prob,
+                       float* __restrict__ grad_occ, const float* __restrict__ aux_t,
+                       const float* __restrict__ aux_nz) {
+  LR_PROLOGUE
+  const float* omap = occ + (size_t)b * HW * L.D;
+  float* gmap = grad_occ + (size_t)b * HW * L.D;
+  float tnz[VEC], nz[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { tnz[v] = 1.f; nz[v] = 0.f; }
+  const int kend = march_end(L, c.lenG);
+  if (aux_t) {            // forward saved the products: skip the recomputation march
+    V<VEC>::ld(aux_t + ((size_t)b * HW + u) * L.D + ch, tnz);
+    V<VEC>::ld(aux_nz + ((size_t)b * HW + u) * L.D + ch, nz);
+  }
+  for (int k0 = 0; !aux_t && k0 < kend; k0 += WPI) {
+    const int k = k0 + slot;
+    if (k < kend) {
+      float gx, gy, len;
+      waypoint(L, c, k, gx, gy, len);
+      if (len < c.lenG) {
+        float x[VEC];
+        sample<VEC>(omap, L.D, ch, bilinear_setup(gx, gy, L.Hb, L.Wb), x);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const float f = 1.f - activate(L.act, x[v]);
+          if (f == 0.f) nz[v] += 1.f; else tnz[v] *= f;
+        }
+      }
+    }
+  }
+  if (!aux_t) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+      for (int off = LPW; off < 32; off <<= 1) {
+        tnz[v] *= __shfl_xor_sync(0xffffffffu, tnz[v], off);
+        nz[v] += __shfl_xor_sync(0xffffffffu, nz[v], off);
+      }
+  }
   float g[VEC], xG[VEC], aG[VEC];
   V<VEC>::ld(grad_prob + ((size_t)b * HW + u) * L.D + ch, g);
   const Bil bG = bilinear_setup(c.cgx, c.cgy, L.Hb, L.Wb);
@@ -323,7 +344,7 @@ __device__ __forceinline__ void pool_accumulate(const LrDims& L, const Cell& c, 
 template <int VEC, int G>
 __global__ void __launch_bounds__(kCellsPerBlock * 32)
 latent_pool_fwd_kernel(LrDims L, const float* __restrict__ prob, const float* __restrict__ feat,
-                       float* __restrict__ pooled) {
+                       float* __restrict__ pooled, float* __restrict__ aux_s) {
   LR_PROLOGUE
   const float* pmap = prob + (size_t)b * HW * L.D;
   const float* fmap = feat + (size_t)b * HW * L.D * G;
@@ -341,6 +362,7 @@ latent_pool_fwd_kernel(LrDims L, const float* __restrict__ prob, const float* __
     for (int v = 0; v < VEC; ++v)
 #pragma unroll
       for (int j = 0; j < G; ++j) o[(ch + v) * G + j] = N[v * G + j] / (S[v] + L.eps);
+    if (aux_s) V<VEC>::st(aux_s + ((size_t)b * HW + u) * L.D + ch, S);
   }
 }
 
@@ -349,20 +371,30 @@ template <int VEC, int G>
 __global__ void __launch_bounds__(kCellsPerBlock * 32)
 latent_pool_bwd_kernel(LrDims L, const float* __restrict__ prob, const float* __restrict__ feat,
                        const float* __restrict__ grad_pooled, float* __restrict__ grad_prob_map,
-                       float* __restrict__ grad_feat) {
+                       float* __restrict__ grad_feat, const float* __restrict__ aux_s,
+                       const float* __restrict__ pooled) {
   LR_PROLOGUE
   const float* pmap = prob + (size_t)b * HW * L.D;
   const float* fmap = feat + (size_t)b * HW * L.D * G;
   float* gpm = grad_prob_map + (size_t)b * HW * L.D;
   float* gfm = grad_feat + (size_t)b * HW * L.D * G;
   float S[VEC], N[VEC * G];
-  pool_accumulate<VEC, G>(L, c, pmap, fmap, ch, slot, WPI, S, N);
+  if (aux_s) {            // forward saved S; N = pooled * (S + eps)
+    V<VEC>::ld(aux_s + ((size_t)b * HW + u) * L.D + ch, S);
+    const float* po = pooled + ((size_t)b * HW + u) * L.D * G;
 #pragma unroll
-  for (int v = 0; v < VEC; ++v)
-    for (int off = LPW; off < 32; off <<= 1) S[v] += __shfl_xor_sync(0xffffffffu, S[v], off);
+    for (int v = 0; v < VEC; ++v)
 #pragma unroll
-  for (int v = 0; v < VEC * G; ++v)
-    for (int off = LPW; off < 32; off <<= 1) N[v] += __shfl_xor_sync(0xffffffffu, N[v], off);
+      for (int j = 0; j < G; ++j) N[v * G + j] = __ldg(po + (ch + v) * G + j) * (S[v] + L.eps);
+  } else {
+    pool_accumulate<VEC, G>(L, c, pmap, fmap, ch, slot, WPI, S, N);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+      for (int off = LPW; off < 32; off <<= 1) S[v] += __shfl_xor_sync(0xffffffffu, S[v], off);
+#pragma unroll
+    for (int v = 0; v < VEC * G; ++v)
+      for (int off = LPW; off < 32; off <<= 1) N[v] += __shfl_xor_sync(0xffffffffu, N[v], off);
+  }
   // pooled_c = N_c / (S_d + eps)
   float gN[VEC * G], gS[VEC];
   const float* gp = grad_pooled + ((size_t)b * HW + u) * L.D * G;
@@ -458,31 +490,68 @@ using namespace vidar;
     }                                                                                  \
   } while (0)
 
-extern "C" int vidar_latent_render_forward(const float* occ, const float* feat, float* prob,
-                                           float* pooled, int bs, int D, int G, int Hb, int Wb,
-                                           int grid_num, float grid_step, float eps, int act,
-                                           void* stream) {
+// aux: optional [3, bs, Hb, Wb, D] floats written by the forward (product of non-zero factors,
+// number of zero factors, sum of sampled probabilities) and read by the backward, which then skips
+// its recomputation marches.  NULL = forward saves nothing / backward recomputes.
+#define AUX_T(a) (a)
+#define AUX_NZ(a, n) ((a) ? (a) + (n) : nullptr)
+#define AUX_S(a, n) ((a) ? (a) + 2 * (n) : nullptr)
+
+static int prob_fwd(const LrDims& L, int vec, const float* occ, float* prob, float* aux, cudaStream_t st) {
+  if (L.ncells == 0) return VIDAR_OK;
+  const size_t n = (size_t)L.bs * L.Hb * L.Wb * L.D;
+  const dim3 grid(lr_blocks(L)), block(kCellsPerBlock * 32);
+  if (vec == 4) latent_prob_fwd_kernel<4><<<grid, block, 0, st>>>(L, occ, prob, AUX_T(aux), AUX_NZ(aux, n));
+  else latent_prob_fwd_kernel<1><<<grid, block, 0, st>>>(L, occ, prob, AUX_T(aux), AUX_NZ(aux, n));
+  return check_launch("LatentRendering.prob_forward");
+}
+
+static int pool_fwd(const LrDims& L, int vec, int G, const float* prob, const float* feat, float* pooled,
+                    float* aux, cudaStream_t st) {
+  if (L.ncells == 0) return VIDAR_OK;
+  const size_t n = (size_t)L.bs * L.Hb * L.Wb * L.D;
+  LR_DISPATCH_VG(latent_pool_fwd_kernel, L, prob, feat, pooled, AUX_S(aux, n));
+  return check_launch("LatentRendering.pool_forward");
+}
+
+static int pool_bwd(const LrDims& L, int vec, int G, const float* prob, const float* feat, const float* pooled,
+                    const float* aux, const float* grad_pooled, float* grad_prob_map, float* grad_feat,
+                    cudaStream_t st) {
+  if (L.ncells == 0) return VIDAR_OK;
+  const size_t n = (size_t)L.bs * L.Hb * L.Wb * L.D;
+  const float* as = (aux && pooled) ? aux + 2 * n : nullptr;
+  LR_DISPATCH_VG(latent_pool_bwd_kernel, L, prob, feat, grad_pooled, grad_prob_map, grad_feat, as, pooled);
+  return check_launch("LatentRendering.pool_backward");
+}
+
+static int prob_bwd(const LrDims& L, int vec, const float* occ, const float* aux, const float* grad_prob_total,
+                    float* grad_occ, cudaStream_t st) {
+  if (L.ncells == 0) return VIDAR_OK;
+  const size_t n = (size_t)L.bs * L.Hb * L.Wb * L.D;
+  const dim3 grid(lr_blocks(L)), block(kCellsPerBlock * 32);
+  if (vec == 4) latent_prob_bwd_kernel<4><<<grid, block, 0, st>>>(L, occ, grad_prob_total, grad_occ, aux, aux ? aux + n : nullptr);
+  else latent_prob_bwd_kernel<1><<<grid, block, 0, st>>>(L, occ, grad_prob_total, grad_occ, aux, aux ? aux + n : nullptr);
+  return check_launch("LatentRendering.prob_backward");
+}
+
+extern "C" int vidar_latent_render_forward(const float* occ, const float* feat, float* prob, float* pooled,
+                                           float* aux, int bs, int D, int G, int Hb, int Wb, int grid_num,
+                                           float grid_step, float eps, int act, void* stream) {
   LrDims L;
   int vec;
   int rc = check_lr(L, bs, D, G, Hb, Wb, grid_num, grid_step, eps, act, vec, "LatentRendering.forward");
   if (rc) return rc;
   VIDAR_REQUIRE(occ && feat && prob && pooled, "LatentRendering.forward: null pointer argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  const dim3 grid(lr_blocks(L)), block(kCellsPerBlock * 32);
-  if (vec == 4) latent_prob_fwd_kernel<4><<<grid, block, 0, st>>>(L, occ, prob);
-  else latent_prob_fwd_kernel<1><<<grid, block, 0, st>>>(L, occ, prob);
-  rc = check_launch("LatentRendering.forward(prob)");
+  rc = prob_fwd(L, vec, occ, prob, aux, (cudaStream_t)stream);
   if (rc) return rc;
-  LR_DISPATCH_VG(latent_pool_fwd_kernel, L, prob, feat, pooled);
-  return check_launch("LatentRendering.forward(pool)");
+  return pool_fwd(L, vec, G, prob, feat, pooled, aux, (cudaStream_t)stream);
 }
 
 extern "C" int vidar_latent_render_backward(const float* occ, const float* feat, const float* prob,
-                                            const float* grad_prob, const float* grad_pooled,
-                                            float* grad_prob_total, float* grad_occ,
+                                            const float* pooled, const float* aux, const float* grad_prob,
+                                            const float* grad_pooled, float* grad_prob_total, float* grad_occ,
                                             float* grad_feat, int bs, int D, int G, int Hb, int Wb,
-                                            int grid_num, float grid_step, float eps, int act,
-                                            void* stream) {
+                                            int grid_num, float grid_step, float eps, int act, void* stream) {
   LrDims L;
   int vec;
   int rc = check_lr(L, bs, D, G, Hb, Wb, grid_num, grid_step, eps, act, vec, "LatentRendering.backward");
@@ -490,77 +559,61 @@ extern "C" int vidar_latent_render_backward(const float* occ, const float* feat,
   VIDAR_REQUIRE(occ && feat && prob && grad_prob && grad_pooled && grad_prob_total && grad_occ && grad_feat,
                 "LatentRendering.backward: null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
-  // grad_prob_total starts as a copy of the upstream grad_prob; phase 2 adds the gradient
-  // that reaches the prob map through the ray pooling; phase 1 consumes the sum.
+  // grad_prob_total starts as a copy of the upstream grad_prob; phase 2 adds the gradient that
+  // reaches the prob map through the ray pooling; phase 1 consumes the sum.
   cudaError_t e = cudaMemcpyAsync(grad_prob_total, grad_prob, sizeof(float) * (size_t)bs * Hb * Wb * D,
                                   cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return set_error(VIDAR_E_CUDA, "LatentRendering.backward: memcpy: %s", cudaGetErrorString(e));
-  LR_DISPATCH_VG(latent_pool_bwd_kernel, L, prob, feat, grad_pooled, grad_prob_total, grad_feat);
-  rc = check_launch("LatentRendering.backward(pool)");
+  rc = pool_bwd(L, vec, G, prob, feat, pooled, aux, grad_pooled, grad_prob_total, grad_feat, st);
   if (rc) return rc;
-  const dim3 grid(lr_blocks(L)), block(kCellsPerBlock * 32);
-  if (vec == 4) latent_prob_bwd_kernel<4><<<grid, block, 0, st>>>(L, occ, grad_prob_total, grad_occ);
-  else latent_prob_bwd_kernel<1><<<grid, block, 0, st>>>(L, occ, grad_prob_total, grad_occ);
-  return check_launch("LatentRendering.backward(prob)");
+  return prob_bwd(L, vec, occ, aux, grad_prob_total, grad_occ, st);
 }
 
 // ---- phase-wise entry points on a cell range: lets the host put a collective between the
 // phases when the BEV cells are sharded over GPUs.
-extern "C" int vidar_latent_prob_forward(const float* occ, float* prob, int bs, int D, int Hb, int Wb,
-                                         int grid_num, float grid_step, int act, long long cell0,
+extern "C" int vidar_latent_prob_forward(const float* occ, float* prob, float* aux, int bs, int D, int Hb,
+                                         int Wb, int grid_num, float grid_step, int act, long long cell0,
                                          long long ncells, void* stream) {
   LrDims L;
   int vec;
   int rc = check_lr(L, bs, D, 1, Hb, Wb, grid_num, grid_step, 0.f, act, vec, "LatentRendering.prob_forward", cell0, ncells);
   if (rc) return rc;
   VIDAR_REQUIRE(occ && prob, "LatentRendering.prob_forward: null pointer argument");
-  if (L.ncells == 0) return VIDAR_OK;
-  const dim3 grid(lr_blocks(L)), block(kCellsPerBlock * 32);
-  if (vec == 4) latent_prob_fwd_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>(L, occ, prob);
-  else latent_prob_fwd_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(L, occ, prob);
-  return check_launch("LatentRendering.prob_forward");
+  return prob_fwd(L, vec, occ, prob, aux, (cudaStream_t)stream);
 }
 
-extern "C" int vidar_latent_pool_forward(const float* prob, const float* feat, float* pooled, int bs, int D,
-                                         int G, int Hb, int Wb, int grid_num, float grid_step, float eps,
-                                         long long cell0, long long ncells, void* stream) {
+extern "C" int vidar_latent_pool_forward(const float* prob, const float* feat, float* pooled, float* aux,
+                                         int bs, int D, int G, int Hb, int Wb, int grid_num, float grid_step,
+                                         float eps, long long cell0, long long ncells, void* stream) {
   LrDims L;
   int vec;
   int rc = check_lr(L, bs, D, G, Hb, Wb, grid_num, grid_step, eps, 1, vec, "LatentRendering.pool_forward", cell0, ncells);
   if (rc) return rc;
   VIDAR_REQUIRE(prob && feat && pooled, "LatentRendering.pool_forward: null pointer argument");
-  if (L.ncells == 0) return VIDAR_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  LR_DISPATCH_VG(latent_pool_fwd_kernel, L, prob, feat, pooled);
-  return check_launch("LatentRendering.pool_forward");
+  return pool_fwd(L, vec, G, prob, feat, pooled, aux, (cudaStream_t)stream);
 }
 
-extern "C" int vidar_latent_pool_backward(const float* prob, const float* feat, const float* grad_pooled,
-                                          float* grad_prob_map, float* grad_feat, int bs, int D, int G,
-                                          int Hb, int Wb, int grid_num, float grid_step, float eps,
-                                          long long cell0, long long ncells, void* stream) {
+extern "C" int vidar_latent_pool_backward(const float* prob, const float* feat, const float* pooled,
+                                          const float* aux, const float* grad_pooled, float* grad_prob_map,
+                                          float* grad_feat, int bs, int D, int G, int Hb, int Wb, int grid_num,
+                                          float grid_step, float eps, long long cell0, long long ncells,
+                                          void* stream) {
   LrDims L;
   int vec;
   int rc = check_lr(L, bs, D, G, Hb, Wb, grid_num, grid_step, eps, 1, vec, "LatentRendering.pool_backward", cell0, ncells);
   if (rc) return rc;
   VIDAR_REQUIRE(prob && feat && grad_pooled && grad_prob_map && grad_feat, "LatentRendering.pool_backward: null pointer argument");
-  if (L.ncells == 0) return VIDAR_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  LR_DISPATCH_VG(latent_pool_bwd_kernel, L, prob, feat, grad_pooled, grad_prob_map, grad_feat);
-  return check_launch("LatentRendering.pool_backward");
+  return pool_bwd(L, vec, G, prob, feat, pooled, aux, grad_pooled, grad_prob_map, grad_feat, (cudaStream_t)stream);
 }
 
-extern "C" int vidar_latent_prob_backward(const float* occ, const float* grad_prob_total, float* grad_occ,
-                                          int bs, int D, int Hb, int Wb, int grid_num, float grid_step,
-                                          int act, long long cell0, long long ncells, void* stream) {
+extern "C" int vidar_latent_prob_backward(const float* occ, const float* aux, const float* grad_prob_total,
+                                          float* grad_occ, int bs, int D, int Hb, int Wb, int grid_num,
+                                          float grid_step, int act, long long cell0, long long ncells,
+                                          void* stream) {
   LrDims L;
   int vec;
   int rc = check_lr(L, bs, D, 1, Hb, Wb, grid_num, grid_step, 0.f, act, vec, "LatentRendering.prob_backward", cell0, ncells);
   if (rc) return rc;
   VIDAR_REQUIRE(occ && grad_prob_total && grad_occ, "LatentRendering.prob_backward: null pointer argument");
-  if (L.ncells == 0) return VIDAR_OK;
-  const dim3 grid(lr_blocks(L)), block(kCellsPerBlock * 32);
-  if (vec == 4) latent_prob_bwd_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>(L, occ, grad_prob_total, grad_occ);
-  else latent_prob_bwd_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(L, occ, grad_prob_total, grad_occ);
-  return check_launch("LatentRendering.prob_backward");
+  return prob_bwd(L, vec, occ, aux, grad_prob_total, grad_occ, (cudaStream_t)stream);
 }

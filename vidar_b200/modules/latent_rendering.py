@@ -33,17 +33,19 @@ class _LatentRenderCore(torch.autograd.Function):
             raise RuntimeError("feat must be [bs, Hb, Wb, pred_height * k]")
         prob = torch.empty_like(occ)
         pooled = torch.empty((bs, Hb * Wb, Ca), dtype=torch.float32, device=occ.device)
+        # forward by-products the backward would otherwise re-march the rays for (3 x 2.56 MB)
+        aux = torch.empty((3,) + tuple(occ.shape), dtype=torch.float32, device=occ.device)
         with torch.cuda.device(occ.device):
             _lib.check(_lib.lib().vidar_latent_render_forward(
-                _lib.ptr(occ), _lib.ptr(feat), _lib.ptr(prob), _lib.ptr(pooled), bs, D, Ca // D, Hb, Wb,
-                int(grid_num), float(grid_step), float(eps), int(act), _lib.stream_ptr(occ.device)))
-        ctx.save_for_backward(occ, feat, prob)
+                _lib.ptr(occ), _lib.ptr(feat), _lib.ptr(prob), _lib.ptr(pooled), _lib.ptr(aux), bs, D, Ca // D,
+                Hb, Wb, int(grid_num), float(grid_step), float(eps), int(act), _lib.stream_ptr(occ.device)))
+        ctx.save_for_backward(occ, feat, prob, pooled, aux)
         ctx.cfg = (int(grid_num), float(grid_step), float(eps), int(act))
         return prob, pooled
 
     @staticmethod
     def backward(ctx, grad_prob, grad_pooled):
-        occ, feat, prob = ctx.saved_tensors
+        occ, feat, prob, pooled, aux = ctx.saved_tensors
         grid_num, grid_step, eps, act = ctx.cfg
         bs, Hb, Wb, D = occ.shape
         Ca = feat.shape[-1]
@@ -54,9 +56,9 @@ class _LatentRenderCore(torch.autograd.Function):
         grad_feat = torch.zeros_like(feat)
         with torch.cuda.device(occ.device):
             _lib.check(_lib.lib().vidar_latent_render_backward(
-                _lib.ptr(occ), _lib.ptr(feat), _lib.ptr(prob), _lib.ptr(grad_prob), _lib.ptr(grad_pooled),
-                _lib.ptr(scratch), _lib.ptr(grad_occ), _lib.ptr(grad_feat), bs, D, Ca // D, Hb, Wb,
-                grid_num, grid_step, eps, act, _lib.stream_ptr(occ.device)))
+                _lib.ptr(occ), _lib.ptr(feat), _lib.ptr(prob), _lib.ptr(pooled), _lib.ptr(aux), _lib.ptr(grad_prob),
+                _lib.ptr(grad_pooled), _lib.ptr(scratch), _lib.ptr(grad_occ), _lib.ptr(grad_feat), bs, D, Ca // D,
+                Hb, Wb, grid_num, grid_step, eps, act, _lib.stream_ptr(occ.device)))
         return grad_occ, grad_feat, None, None, None, None
 
 
@@ -86,23 +88,24 @@ class _ShardedLatentRenderCore(torch.autograd.Function):
         c0, n = _ShardedLatentRenderCore._range(bs * Hb * Wb, group)
         prob = torch.zeros_like(occ)
         pooled = torch.zeros((bs, Hb * Wb, Ca), dtype=torch.float32, device=occ.device)
+        aux = torch.empty((3,) + tuple(occ.shape), dtype=torch.float32, device=occ.device)   # only this rank's cells are filled / read
         L = _lib.lib()
         with torch.cuda.device(occ.device):
             st = _lib.stream_ptr(occ.device)
-            _lib.check(L.vidar_latent_prob_forward(_lib.ptr(occ), _lib.ptr(prob), bs, D, Hb, Wb, int(grid_num),
-                                                   float(grid_step), int(act), c0, n, st))
+            _lib.check(L.vidar_latent_prob_forward(_lib.ptr(occ), _lib.ptr(prob), _lib.ptr(aux), bs, D, Hb, Wb,
+                                                   int(grid_num), float(grid_step), int(act), c0, n, st))
             dist.all_reduce(prob, group=group)
-            _lib.check(L.vidar_latent_pool_forward(_lib.ptr(prob), _lib.ptr(feat), _lib.ptr(pooled), bs, D, Ca // D,
-                                                   Hb, Wb, int(grid_num), float(grid_step), float(eps), c0, n, st))
+            _lib.check(L.vidar_latent_pool_forward(_lib.ptr(prob), _lib.ptr(feat), _lib.ptr(pooled), _lib.ptr(aux), bs, D,
+                                                   Ca // D, Hb, Wb, int(grid_num), float(grid_step), float(eps), c0, n, st))
             dist.all_reduce(pooled, group=group)
-        ctx.save_for_backward(occ, feat, prob)
+        ctx.save_for_backward(occ, feat, prob, pooled, aux)
         ctx.cfg = (int(grid_num), float(grid_step), float(eps), int(act), group, c0, n)
         return prob, pooled
 
     @staticmethod
     def backward(ctx, grad_prob, grad_pooled):
         import torch.distributed as dist
-        occ, feat, prob = ctx.saved_tensors
+        occ, feat, prob, pooled, aux = ctx.saved_tensors
         grid_num, grid_step, eps, act, group, c0, n = ctx.cfg
         bs, Hb, Wb, D = occ.shape
         Ca = feat.shape[-1]
@@ -115,17 +118,17 @@ class _ShardedLatentRenderCore(torch.autograd.Function):
         L = _lib.lib()
         with torch.cuda.device(occ.device):
             st = _lib.stream_ptr(occ.device)
-            _lib.check(L.vidar_latent_pool_backward(_lib.ptr(prob), _lib.ptr(feat), _lib.ptr(grad_pooled), _lib.ptr(gpm),
-                                                    _lib.ptr(gfe), bs, D, Ca // D, Hb, Wb, grid_num, grid_step, eps,
-                                                    c0, n, st))
+            _lib.check(L.vidar_latent_pool_backward(_lib.ptr(prob), _lib.ptr(feat), _lib.ptr(pooled), _lib.ptr(aux),
+                                                    _lib.ptr(grad_pooled), _lib.ptr(gpm), _lib.ptr(gfe), bs, D, Ca // D,
+                                                    Hb, Wb, grid_num, grid_step, eps, c0, n, st))
             if both is not None:
                 dist.all_reduce(both, group=group)
             else:
                 dist.all_reduce(gpm, group=group)
                 dist.all_reduce(gfe, group=group)
             total = (gpm + grad_prob.float()).contiguous()
-            _lib.check(L.vidar_latent_prob_backward(_lib.ptr(occ), _lib.ptr(total), _lib.ptr(grad_occ), bs, D, Hb, Wb,
-                                                    grid_num, grid_step, act, c0, n, st))
+            _lib.check(L.vidar_latent_prob_backward(_lib.ptr(occ), _lib.ptr(aux), _lib.ptr(total), _lib.ptr(grad_occ), bs, D,
+                                                    Hb, Wb, grid_num, grid_step, act, c0, n, st))
             dist.all_reduce(grad_occ, group=group)
         return grad_occ, gfe.clone() if both is not None else gfe, None, None, None, None, None
 
