@@ -447,137 +447,141 @@ def run_ours(args):
 # CPU arm: the reference's CPU path for MSDA (multi_scale_deformable_attn_pytorch formula) and
 # the C port of the ray-caster (the reference has no CPU ray-caster), on a bounded sample.
 # ------------------------------------------------------------------------------------------
-CPU_Q_SMALL, CPU_Q_LARGE = 2000, 8000   # two samples of one camera -> per-camera fixed + per-query cost
+class CpuArm:
+    """The reference's CPU formulas for the step, on a bounded sample extrapolated to the full step.
+      MSDA fwd+bwd     torch CPU grid_sample formula (= mmcv's multi_scale_deformable_attn_pytorch, the
+                       reference's own CPU path) on ONE camera at two query counts q and 4q; the affine fit
+                       t(Q) = a + b*Q gives 6*a + 240000*b (each camera pays the cost of touching its
+                       31.6 MB value / grad_value once);
+      LatentRendering  reference formula (torch CPU) on `cells` of the 40000 BEV cells, scaled;
+      head sampler+CE  reference formula (torch CPU) on `rays` of the 30000 rays, scaled;
+      dvr.render       C/OpenMP port (oracle/dvr_ref.c) on all 30000 rays.
+    `scale` in (0, 1] shrinks the samples so that K steps fit a time budget; the number of torch threads is
+    calibrated once (more threads than ~32 is slower for these ops on many-core hosts)."""
+    Q0, CELLS0, RAYS0 = 2000, 4000, 6000
+
+    def __init__(self):
+        full = sca_like_inputs(torch.device("cpu"), cams=1, Q=BEV_Q, seed=0)
+        sl = slice(BEV_Q // 2, BEV_Q // 2 + 4 * self.Q0)
+        self.d = dict(value=full["value"], shapes=full["shapes"], lsi=full["lsi"],
+                      loc=full["loc"][:, sl].contiguous(), attn=full["attn"][:, sl].contiguous(),
+                      grad_out=full["grad_out"][:, sl].contiguous())
+        g = torch.Generator().manual_seed(3)
+        mk = lambda f: f(1, GRID[1], GRID[2], GRID[0], generator=g)
+        self.lat = (mk(torch.randn), mk(torch.randn), mk(torch.rand))
+        self.rays = ray_inputs()
+        self.scale = 1.0
+        self.threads = self._calibrate_threads()
+
+    def _calibrate_threads(self):
+        cores = os.cpu_count() or 1
+        best, best_t = cores, None
+        for n in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
+            torch.set_num_threads(n)
+            self._msda(250)                       # warm
+            t = self._msda(500)
+            if best_t is None or t < best_t:
+                best, best_t = n, t
+        torch.set_num_threads(best)
+        return best
+
+    def _msda(self, q):
+        from oracle import msda_ref
+        d = self.d
+        t0 = time.perf_counter()
+        v = d["value"].detach().requires_grad_(True)
+        loc = d["loc"][:, :q].detach().contiguous().requires_grad_(True)
+        aw = d["attn"][:, :q].detach().contiguous().requires_grad_(True)
+        out = msda_ref.msda_grid_sample(v, d["shapes"], loc, aw)
+        out.backward(d["grad_out"][:, :q].contiguous())
+        return time.perf_counter() - t0
+
+    def _latent(self, cells):
+        from oracle import latent_render_ref as lr
+        occ, feat, probmap = self.lat
+        t0 = time.perf_counter()
+        o, f = occ.detach().requires_grad_(True), feat.detach().requires_grad_(True)
+        p, q = lr.latent_core(o, f, LR_GRID_NUM, 0.5, 1e-3, "sigmoid", cells=slice(0, cells), prob_map=probmap)
+        (p.sum() + q.sum()).backward()
+        return (time.perf_counter() - t0) * (GRID[1] * GRID[2] / cells)
+
+    def _ray_ce(self, rays_n):
+        from oracle import ray_head_ref as rr
+        sigma, origin, points, tindex = self.rays
+        t0 = time.perf_counter()
+        s = torch.from_numpy(sigma[0]).requires_grad_(True)
+        tot, n = 0, 0
+        for f in range(FRAMES):
+            sel = np.flatnonzero(tindex[0] == f)[: max(1, rays_n // FRAMES)]
+            lg, ln, vd = rr.sample_frame(s[f], torch.from_numpy(origin[0, f]), torch.from_numpy(points[0][sel]), WAYPOINTS, 1.0)
+            tot = tot - torch.log_softmax(lg[vd], -1)[:, 0].sum()
+            n += len(sel)
+        tot.backward()
+        return (time.perf_counter() - t0) * (RAYS / n)
+
+    def sizes(self):
+        q = max(250, int(self.Q0 * self.scale))
+        return q, max(500, int(self.CELLS0 * self.scale)), max(600, int(self.RAYS0 * self.scale))
+
+    def step(self):
+        """-> (estimated seconds for the FULL step, seconds of CPU work spent, per-part estimates)."""
+        from oracle import dvr_ref
+        q, cells, rays_n = self.sizes()
+        t00 = time.perf_counter()
+        ts, tl = self._msda(q), self._msda(4 * q)
+        b = max(tl - ts, 0.0) / (3 * q)
+        a = max(ts - b * q, 0.0)
+        parts = {"msda": NUM_CAMS * a + NUM_CAMS * BEV_Q * b, "latent_render": self._latent(cells),
+                 "ray_ce": self._ray_ce(rays_n)}
+        t0 = time.perf_counter()
+        dvr_ref.render(*self.rays, "l2")
+        parts["dvr_render"] = time.perf_counter() - t0
+        return sum(parts.values()), time.perf_counter() - t00, parts
+
+    def run(self, steps, warmup, budget_s):
+        """`warmup` untimed + `steps` timed sample-steps within about `budget_s` seconds of CPU work."""
+        _, spent, _ = self.step()                      # calibration step at full sample size (untimed)
+        self.scale = min(1.0, max(0.05, budget_s / max(steps + warmup, 1) / max(spent, 1e-6)))
+        for _ in range(max(warmup - 1, 0)):
+            self.step()
+        est = [self.step() for _ in range(steps)]
+        return est
+
+    def describe(self, est):
+        from oracle import dvr_ref
+        q, cells, rays_n = self.sizes()
+        parts = {k: float(np.mean([e[2][k] for e in est])) for k in est[0][2]}
+        return (f"per step {np.mean([e[1] for e in est]):.1f} s of CPU work on {self.threads} torch threads / "
+                f"{dvr_ref.num_threads()} OpenMP threads: MSDA fwd+bwd (torch CPU grid_sample formula = the reference's CPU "
+                f"path) on 1 camera at {q} and {4 * q} queries, affine fit -> 6 cams x 40000 queries; LatentRendering core "
+                f"(reference formula) on {cells}/40000 cells, scaled; head ray sampler+CE (reference formula) on "
+                f"{rays_n}/30000 rays, scaled; C/OpenMP port of dvr.render on all 30000 rays.  Full-step estimates (s): "
+                + ", ".join(f"{k}={v:.2f}" for k, v in parts.items()))
 
 
-def _cpu_msda(d, q):
-    from oracle import msda_ref
-    t0 = time.perf_counter()
-    v = d["value"].detach().requires_grad_(True)
-    loc = d["loc"][:, :q].detach().contiguous().requires_grad_(True)
-    aw = d["attn"][:, :q].detach().contiguous().requires_grad_(True)
-    out = msda_ref.msda_grid_sample(v, d["shapes"], loc, aw)
-    out.backward(d["grad_out"][:, :q].contiguous())
-    return time.perf_counter() - t0
-
-
-CPU_LR_CELLS = 4000      # of 40000 BEV cells
-CPU_CE_RAYS = 6000       # of 30000 rays
-
-
-def _cpu_latent(lat):
-    """LatentRendering fwd+bwd on the first CPU_LR_CELLS cells (both phases; phase 2 samples a
-    full-size prob map); scaled by 40000/CPU_LR_CELLS."""
-    import types
-
-    import torch.nn.functional as F  # noqa: F401
-    from oracle import latent_render_ref as lr
-    occ, feat, probmap = lat
-    t0 = time.perf_counter()
-    o = occ.detach().requires_grad_(True)
-    f = feat.detach().requires_grad_(True)
-    p, q = lr.latent_core(o, f, LR_GRID_NUM, 0.5, 1e-3, "sigmoid", cells=slice(0, CPU_LR_CELLS), prob_map=probmap)
-    (p.sum() + q.sum()).backward()
-    return (time.perf_counter() - t0) * (GRID[1] * GRID[2] / CPU_LR_CELLS)
-
-
-def _cpu_ray_ce(rays):
-    from oracle import ray_head_ref as rr
-    sigma, origin, points, tindex = rays
-    t0 = time.perf_counter()
-    s = torch.from_numpy(sigma[0]).requires_grad_(True)
-    tot = 0
-    n = 0
-    for f in range(FRAMES):
-        sel = np.flatnonzero(tindex[0] == f)[: CPU_CE_RAYS // FRAMES]
-        lg, ln, vd = rr.sample_frame(s[f], torch.from_numpy(origin[0, f]), torch.from_numpy(points[0][sel]), WAYPOINTS, 1.0)
-        tot = tot - torch.log_softmax(lg[vd], -1)[:, 0].sum()
-        n += len(sel)
-    tot.backward()
-    return (time.perf_counter() - t0) * (RAYS / n)
-
-
-def cpu_step(inputs):
-    """One bounded sample of every part of the step, extrapolated to the full step.
-      MSDA fwd+bwd: one camera at two query counts; affine fit t(Q) = a + b*Q -> 6*a + 240000*b
-        (each camera pays the per-call cost of touching its 31.6 MB value / grad_value once);
-      LatentRendering core fwd+bwd: CPU_LR_CELLS of the 40000 cells, scaled;
-      head ray sampler + CE fwd+bwd: CPU_CE_RAYS of the 30000 rays, scaled;
-      dvr.render: all 30000 rays (C/OpenMP port).
-    Returns (estimated seconds for the FULL step, sample seconds, per-part estimates)."""
-    from oracle import dvr_ref
-    d, rays, lat = inputs
-    t00 = time.perf_counter()
-    ts = _cpu_msda(d, CPU_Q_SMALL)
-    tl = _cpu_msda(d, CPU_Q_LARGE)
-    b = max(tl - ts, 0.0) / (CPU_Q_LARGE - CPU_Q_SMALL)
-    a = max(ts - b * CPU_Q_SMALL, 0.0)
-    t_msda = NUM_CAMS * a + NUM_CAMS * BEV_Q * b
-    t_lat = _cpu_latent(lat)
-    t_ce = _cpu_ray_ce(rays)
-    t0 = time.perf_counter()
-    dvr_ref.render(*rays, "l2")
-    t_dvr = time.perf_counter() - t0
-    parts = {"msda": t_msda, "latent_render": t_lat, "ray_ce": t_ce, "dvr_render": t_dvr}
-    return t_msda + t_lat + t_ce + t_dvr, time.perf_counter() - t00, parts
-
-
-def cpu_inputs():
-    full = sca_like_inputs(torch.device("cpu"), cams=1, Q=BEV_Q, seed=0)
-    sl = slice(BEV_Q // 2, BEV_Q // 2 + CPU_Q_LARGE)
-    d = dict(value=full["value"], shapes=full["shapes"], lsi=full["lsi"],
-             loc=full["loc"][:, sl].contiguous(), attn=full["attn"][:, sl].contiguous(),
-             grad_out=full["grad_out"][:, sl].contiguous())
-    g = torch.Generator().manual_seed(3)
-    lat = (torch.randn(1, GRID[1], GRID[2], GRID[0], generator=g), torch.randn(1, GRID[1], GRID[2], GRID[0], generator=g),
-           torch.rand(1, GRID[1], GRID[2], GRID[0], generator=g))
-    return d, ray_inputs(), lat
-
-
-def _cpu_sample_text(est):
-    from oracle import dvr_ref
-    parts = {k: float(np.mean([e[2][k] for e in est])) for k in est[0][2]}
-    return (f"per step ({np.mean([e[1] for e in est]):.1f} s of CPU work): MSDA fwd+bwd (torch CPU grid_sample formula = "
-            f"the reference's CPU path) on 1 camera at {CPU_Q_SMALL} and {CPU_Q_LARGE} queries, affine fit -> 6 cams x 40000 "
-            f"queries; LatentRendering core (reference formula, torch CPU) on {CPU_LR_CELLS}/40000 cells, scaled; head ray "
-            f"sampler+CE (reference formula, torch CPU) on {CPU_CE_RAYS}/30000 rays, scaled; C/OpenMP port of dvr.render on "
-            f"all 30000 rays ({dvr_ref.num_threads()} threads).  Full-step estimates (s): "
-            + ", ".join(f"{k}={v:.2f}" for k, v in parts.items()))
-
-
-def cpu_baseline(sample_only=False, steps=2, warmup=1):
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    inputs = cpu_inputs()
-    est = []
-    for i in range(warmup + steps):
-        r = cpu_step(inputs)
-        if i >= warmup:
-            est.append(r)
+def cpu_baseline(sample_only=False, steps=2, warmup=1, budget_s=25.0):
+    arm = CpuArm()
+    est = arm.run(steps, warmup, budget_s)
     full_s = float(np.mean([e[0] for e in est]))
-    return {"value": RAYS / full_s, "unit": "rays/s", "cores": cores, "kind": "port",
-            "est_ms_per_step": full_s * 1e3, "sample": _cpu_sample_text(est)}
+    return {"value": RAYS / full_s, "unit": "rays/s", "cores": arm.threads, "kind": "port",
+            "est_ms_per_step": full_s * 1e3, "sample": arm.describe(est)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    inputs = cpu_inputs()
-    for _ in range(args.warmup):
-        cpu_step(inputs)
-    est = [cpu_step(inputs) for _ in range(args.steps)]
+    arm = CpuArm()
+    est = arm.run(args.steps, args.warmup, budget_s=150.0)      # the whole run stays within a few minutes
     full_s = float(np.mean([e[0] for e in est]))
     value = RAYS / full_s
-    sample = _cpu_sample_text(est)
+    sample = arm.describe(est)
     _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_s * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator as the GPU arm)",
         "config": {"workload": WORKLOAD},
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": arm.threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 

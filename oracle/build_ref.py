@@ -68,46 +68,57 @@ def so_path(name):
     return os.path.join(OUT, name + ".so")
 
 
-def build(names=None, force=False):
-    if not os.path.isdir(REF):
-        return {}        # GPU box: use the prebuilt files
+def _build_one(name, force=False):
+    sub, files = TARGETS[name]
+    if os.path.exists(so_path(name)) and not force:
+        return so_path(name)
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
-    os.environ.setdefault("MAX_JOBS", "4")
+    os.environ.setdefault("MAX_JOBS", "2")
     from torch.utils import cpp_extension
     os.makedirs(OUT, exist_ok=True)
-    built = {}
-    if not names or "ref_knn_cpu" in names:
-        k = build_knn_cpu(force)
-        if k:
-            built["ref_knn_cpu"] = k
-    for name, (sub, files) in TARGETS.items():
-        if names and name not in names:
-            continue
-        if os.path.exists(so_path(name)) and not force:
-            built[name] = so_path(name)
-            continue
-        tmp = tempfile.mkdtemp(prefix=f"{name}_src_")
-        bdir = tempfile.mkdtemp(prefix=f"{name}_build_")
-        try:
-            srcs = []
-            for f in files:
-                with open(os.path.join(REF, sub, f)) as fh:
-                    text = _patch(fh.read())
-                dst = os.path.join(tmp, f)
-                with open(dst, "w") as fh:
-                    fh.write(text)
-                srcs.append(dst)
-            cpp_extension.load(
-                name=name, sources=srcs, build_directory=bdir, verbose=False,
-                extra_cuda_cflags=["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"]
-                + EXTRA_FLAGS.get(name, []),
-                is_python_module=False)
-            shutil.copy(os.path.join(bdir, name + ".so"), so_path(name))
-            built[name] = so_path(name)
-        finally:
-            shutil.rmtree(tmp, ignore_errors=True)
-            shutil.rmtree(bdir, ignore_errors=True)
-    return built
+    tmp = tempfile.mkdtemp(prefix=f"{name}_src_")
+    bdir = tempfile.mkdtemp(prefix=f"{name}_build_")
+    try:
+        srcs = []
+        for f in files:
+            with open(os.path.join(REF, sub, f)) as fh:
+                text = _patch(fh.read())
+            dst = os.path.join(tmp, f)
+            with open(dst, "w") as fh:
+                fh.write(text)
+            srcs.append(dst)
+        cpp_extension.load(
+            name=name, sources=srcs, build_directory=bdir, verbose=False,
+            extra_cuda_cflags=["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"]
+            + EXTRA_FLAGS.get(name, []),
+            is_python_module=False)
+        shutil.copy(os.path.join(bdir, name + ".so"), so_path(name))
+        return so_path(name)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+        shutil.rmtree(bdir, ignore_errors=True)
+
+
+def build(names=None, force=False, parallel=True):
+    """Build the missing reference extensions (each ~4 min of ptxas on the MAX_D local arrays); the
+    targets are independent, so they are compiled in parallel child processes."""
+    if not os.path.isdir(REF):
+        return {}        # GPU box: use the prebuilt files
+    import subprocess
+    os.makedirs(OUT, exist_ok=True)
+    want = [n for n in list(TARGETS) + ["ref_knn_cpu"] if not names or n in names]
+    todo = [n for n in want if force or not os.path.exists(so_path(n))]
+    if parallel and len(todo) > 1:
+        procs = [(n, subprocess.Popen([sys.executable, os.path.abspath(__file__), "--one", n] + (["--force"] if force else []),
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)) for n in todo]
+        for n, p in procs:
+            _, err = p.communicate()
+            if p.returncode != 0:
+                raise RuntimeError(f"building {n} failed:\n{err[-2000:]}")
+    else:
+        for n in todo:
+            build_knn_cpu(force) if n == "ref_knn_cpu" else _build_one(n, force)
+    return {n: so_path(n) for n in want if os.path.exists(so_path(n))}
 
 
 def load(name):
@@ -125,4 +136,9 @@ def load(name):
 
 
 if __name__ == "__main__":
-    print(build(names=sys.argv[1:] or None, force=False))
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    force = "--force" in sys.argv
+    if "--one" in sys.argv:
+        print(build_knn_cpu(force) if argv[0] == "ref_knn_cpu" else _build_one(argv[0], force))
+    else:
+        print(build(names=argv or None, force=force))
