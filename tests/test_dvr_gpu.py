@@ -159,3 +159,48 @@ def test_full_size_properties(cuda):
     fd = ((pp - pm).double().sum() / (2 * eps)).item()
     an = (sg.grad.double() * direction.double()).sum().item()
     assert fd == pytest.approx(an, rel=2e-3)
+
+
+def _outside_origin_case(seed=11, M=800):
+    """Origins OUTSIDE the volume (the warp-per-ray kernels hand these to their serial path): rays
+    that enter, rays that never enter, rays that end before entering, degenerate zero-length rays."""
+    rng = np.random.default_rng(seed)
+    sigma = rng.uniform(0, 1, (1, 2, 6, 30, 28)).astype(np.float32)
+    origin = np.array([[[-7.3, 12.2, 2.5], [14.1, 40.6, 9.7]]], np.float32)       # frame 0: x<0 ; frame 1: y,z beyond
+    points = (rng.uniform(0, 1, (1, M, 3)) * np.array([40, 44, 10]) - np.array([6, 7, 2])).astype(np.float32)
+    tindex = rng.integers(0, 2, (1, M)).astype(np.float32)
+    points[0, :5] = origin[0, tindex[0, :5].astype(int)]        # zero-length rays (NaN direction)
+    points[0, 5:25] = origin[0, tindex[0, 5:25].astype(int)] + rng.normal(0, 0.5, (20, 3)).astype(np.float32)  # end before entering
+    tindex[0, -9:] = -1
+    return sigma, origin, points, tindex
+
+
+def test_origin_outside_volume_uses_serial_path_and_matches_oracle(cuda):
+    sigma, origin, points, tindex = _outside_origin_case()
+    s, o, p, t = _t(cuda, sigma, origin, points, tindex)
+    for phase in ("test", "train"):
+        rp, rg = dvr_ref.render_forward(sigma, origin, points, tindex, None, phase)
+        pred, gt = render.dvr.render_forward(s, o, p, t, list(sigma.shape[1:]), phase)
+        a, b = pred.cpu().numpy(), rp
+        assert (np.isnan(a) == np.isnan(b)).all() and ((a == -1) == (b == -1)).all()
+        ok = ~np.isnan(b)
+        _close(a[ok], b[ok], f"pred {phase}", rtol=1e-5)
+        _close(gt.cpu().numpy()[ok], rg[ok], f"gt {phase}", rtol=1e-5)
+    assert 0.05 < (rp == -1).mean() < 0.95          # both outcomes are exercised
+    rp, rg, rgrad = dvr_ref.render(sigma, origin, points, tindex, "l1")
+    pred, gt, grad = render.dvr.render(s, o, p, t, "l1")
+    ok = ~np.isnan(rp)
+    _close(pred.cpu().numpy()[ok], rp[ok], "pred render", rtol=1e-5)
+    fin = np.isfinite(rgrad)
+    _close(grad.cpu().numpy()[fin], rgrad[fin], "grad_sigma")
+
+
+def test_all_padded_and_single_ray(cuda):
+    sigma, origin, points, tindex = dvr_inputs_cfg1(seed=3, M=64, pad=0)
+    s, o, p, t = _t(cuda, sigma, origin, points, tindex)
+    t_pad = torch.full_like(t, -1.0)
+    pred, gt, grad = render.dvr.render(s, o, p, t_pad, "l2")
+    assert float(pred.max()) == -1 and float(gt.max()) == -1 and float(grad.abs().sum()) == 0
+    pred1, gt1, _ = render.dvr.render(s, o, p[:, :1].contiguous(), t[:, :1].contiguous(), "l2")
+    rp, rg, _ = dvr_ref.render(sigma, origin, points[:, :1], tindex[:, :1], "l2")
+    _close(pred1, rp, "single ray", rtol=1e-5)

@@ -154,3 +154,25 @@ def test_full_size_properties(cuda):
     msda.ext_module.ms_deform_attn_backward(d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"], go, gv, gl, ga, im2col_step=64)
     # d/dvalue of sum(out) == what forward computes on an all-ones map
     torch.testing.assert_close(gv.double().sum(), o3.double().sum(), rtol=1e-5, atol=1e-3)
+
+
+def test_edge_inputs(cuda):
+    """Empty query set, NaN / far-outside sampling locations, zero weights."""
+    shapes, lsi = level_tensors(((5, 7), (3, 4)), device=cuda)
+    K = 5 * 7 + 3 * 4
+    value = torch.randn(2, K, 8, 32, device=cuda)
+    empty = msda.ext_module.ms_deform_attn_forward(value, shapes, lsi, torch.zeros(2, 0, 8, 2, 4, 2, device=cuda),
+                                                   torch.zeros(2, 0, 8, 2, 4, device=cuda), im2col_step=64)
+    assert empty.shape == (2, 0, 256)
+    loc = torch.rand(2, 9, 8, 2, 4, 2, device=cuda)
+    loc[0, :3] = float("nan")            # NaN coordinates contribute nothing (comparisons are false)
+    loc[1, 4:] = 37.5                    # far outside
+    attn = torch.softmax(torch.randn(2, 9, 8, 8, device=cuda), -1).view(2, 9, 8, 2, 4)
+    out = msda.ext_module.ms_deform_attn_forward(value, shapes, lsi, loc, attn, im2col_step=64)
+    assert torch.isfinite(out).all()
+    assert float(out[0, :3].abs().max()) == 0 and float(out[1, 4:].abs().max()) == 0
+    gv = torch.zeros_like(value)
+    gl = torch.full_like(loc, 5.0)
+    ga = torch.full_like(attn, 5.0)
+    msda.ext_module.ms_deform_attn_backward(value, shapes, lsi, loc, attn, torch.ones(2, 9, 256, device=cuda), gv, gl, ga, im2col_step=64)
+    assert float(gl[0, :3].abs().max()) == 0 and float(ga[1, 4:].abs().max()) == 0 and torch.isfinite(gv).all()
