@@ -141,8 +141,12 @@ static int trace_ray(const dims_t* D, int variant, const float* sigma, const flo
       else           { dcur = tmz; vz += sz; tmz += tdz; }
     }
     if (rounded) {
+      /* nvcc's default -fmad=true contracts the reference's `path_v += max(0,_d-last_d)*d`
+       * (dvr.cu:253-255) into one DFMA.  The single rounding matters: an origin with a .5
+       * fractional part puts every crossing of that axis exactly on a round() tie, so the
+       * recorded voxel depends on the last ulp.  fma() reproduces the reference binary. */
       const double adv = fmax(0.0, dcur - last_d);
-      fx += adv * dx; fy += adv * dy; fz += adv * dz;
+      fx = fma(adv, dx, fx); fy = fma(adv, dy, fy); fz = fma(adv, dz, fz);
     }
     if (inside) {
       const double s = sg[((size_t)S->pz[count] * D->Y + S->py[count]) * D->X + S->px[count]];

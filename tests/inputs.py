@@ -69,3 +69,23 @@ def dvr_inputs_lidar(M=30000, T=3, grid=(16, 200, 200), seed=0, N=1, pad=0):
         points[:, -pad:] = np.nan
         tindex[:, -pad:] = -1
     return sigma, origin, points, tindex
+
+
+def dvr_inputs_outside(seed=11, M=800, zero_length=True):
+    """Origins OUTSIDE the volume (the warp-per-ray kernels hand these to their serial path): rays
+    that enter, rays that never enter, rays that end before entering and -- with `zero_length` --
+    degenerate zero-length rays.  Frame 0's z origin has a .5 fraction, which puts the rounded-path
+    variants' z crossings exactly on round() ties (the FMA in the path advance decides them).
+    The reference itself never terminates on a zero-length ray that starts outside (dvr.cu:188-227:
+    `last_d > NaN` is never true), so the golden fixture is generated with zero_length=False."""
+    rng = np.random.default_rng(seed)
+    sigma = rng.uniform(0, 1, (1, 2, 6, 30, 28)).astype(np.float32)
+    origin = np.array([[[-7.3, 12.2, 2.5], [14.1, 40.6, 9.7]]], np.float32)       # frame 0: x<0 ; frame 1: y,z beyond
+    points = (rng.uniform(0, 1, (1, M, 3)) * np.array([40, 44, 10]) - np.array([6, 7, 2])).astype(np.float32)
+    tindex = rng.integers(0, 2, (1, M)).astype(np.float32)
+    points[0, :5] = origin[0, tindex[0, :5].astype(int)]        # zero-length rays (NaN direction)
+    points[0, 5:25] = origin[0, tindex[0, 5:25].astype(int)] + rng.normal(0, 0.5, (20, 3)).astype(np.float32)  # end before entering
+    tindex[0, -9:] = -1
+    if not zero_length:
+        tindex[0, :5] = -1
+    return sigma, origin, points, tindex

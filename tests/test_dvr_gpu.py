@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import dvr_ref
-from tests.inputs import dvr_inputs_cfg1, dvr_inputs_lidar
+from tests.inputs import dvr_inputs_cfg1, dvr_inputs_lidar, dvr_inputs_outside
 from vidar_b200 import render
 
 pytestmark = pytest.mark.gpu
@@ -161,22 +161,8 @@ def test_full_size_properties(cuda):
     assert fd == pytest.approx(an, rel=2e-3)
 
 
-def _outside_origin_case(seed=11, M=800):
-    """Origins OUTSIDE the volume (the warp-per-ray kernels hand these to their serial path): rays
-    that enter, rays that never enter, rays that end before entering, degenerate zero-length rays."""
-    rng = np.random.default_rng(seed)
-    sigma = rng.uniform(0, 1, (1, 2, 6, 30, 28)).astype(np.float32)
-    origin = np.array([[[-7.3, 12.2, 2.5], [14.1, 40.6, 9.7]]], np.float32)       # frame 0: x<0 ; frame 1: y,z beyond
-    points = (rng.uniform(0, 1, (1, M, 3)) * np.array([40, 44, 10]) - np.array([6, 7, 2])).astype(np.float32)
-    tindex = rng.integers(0, 2, (1, M)).astype(np.float32)
-    points[0, :5] = origin[0, tindex[0, :5].astype(int)]        # zero-length rays (NaN direction)
-    points[0, 5:25] = origin[0, tindex[0, 5:25].astype(int)] + rng.normal(0, 0.5, (20, 3)).astype(np.float32)  # end before entering
-    tindex[0, -9:] = -1
-    return sigma, origin, points, tindex
-
-
 def test_origin_outside_volume_uses_serial_path_and_matches_oracle(cuda):
-    sigma, origin, points, tindex = _outside_origin_case()
+    sigma, origin, points, tindex = dvr_inputs_outside()
     s, o, p, t = _t(cuda, sigma, origin, points, tindex)
     for phase in ("test", "train"):
         rp, rg = dvr_ref.render_forward(sigma, origin, points, tindex, None, phase)

@@ -19,12 +19,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import build_ref  # noqa: E402
-from tests.inputs import dvr_inputs_cfg1, dvr_inputs_lidar  # noqa: E402
+from tests.inputs import dvr_inputs_cfg1, dvr_inputs_lidar, dvr_inputs_outside  # noqa: E402
 
 CASES = {
     "cfg1_int": lambda: dvr_inputs_cfg1(seed=0, integer_origin=True),
     "cfg1_frac": lambda: dvr_inputs_cfg1(seed=0, integer_origin=False),
     "lidar_small": lambda: dvr_inputs_lidar(M=1500, T=2, grid=(8, 64, 64), seed=5, pad=12),
+    "outside": lambda: dvr_inputs_outside(zero_length=False),
 }
 
 
@@ -41,7 +42,10 @@ def main():
     dvxlr = build_ref.load("ref_dvxlr")
     dvxlr_v2 = build_ref.load("ref_dvxlr_v2")
     dev = torch.device("cuda:0")
+    only = set(sys.argv[1:])
     for name, make in CASES.items():
+        if only and name not in only:
+            continue
         sigma, origin, points, tindex = make()
         rng = np.random.default_rng(123)
         regul = rng.standard_normal(sigma.shape).astype(np.float32)
