@@ -59,11 +59,26 @@ def pred_case(seed=2, bs=1, frames=2):
                 spatial_shapes=shapes, level_start_index=lsi, grad=torch.randn(bs, Q, E, generator=g))
 
 
+def custom_case(seed=3, bs=2, boxes=False, nq=30):
+    """Detection-decoder layout: sequence-first query/value, one BEV level; `boxes` uses the
+    4-component reference boxes (cx, cy, w, h) branch (decoder.py:317-321)."""
+    g = torch.Generator().manual_seed(seed)
+    K = BEV[0] * BEV[1]
+    shapes, lsi = levels((BEV,))
+    ref = torch.rand(bs, nq, 1, 2, generator=g)
+    if boxes:
+        ref = torch.cat([ref, 0.1 + 0.3 * torch.rand(bs, nq, 1, 2, generator=g)], -1)
+    return dict(query=torch.randn(nq, bs, E, generator=g), query_pos=0.1 * torch.randn(nq, bs, E, generator=g),
+                value=torch.randn(K, bs, E, generator=g), reference_points=ref,
+                spatial_shapes=shapes, level_start_index=lsi, grad=torch.randn(nq, bs, E, generator=g))
+
+
 SCA_CFG = dict(type="SpatialCrossAttention", pc_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], dropout=0.0,
                deformable_attention=dict(type="MSDeformableAttention3D", embed_dims=E, num_points=8, num_levels=4),
                embed_dims=E)
 TSA_CFG = dict(type="TemporalSelfAttention", embed_dims=E, num_levels=1, dropout=0.0)
 PRED_CFG = dict(type="PredictionMSDeformableAttention", embed_dims=E, num_levels=2, dropout=0.0)
+CUSTOM_CFG = dict(type="CustomMSDeformableAttention", embed_dims=E, num_levels=1, dropout=0.0)
 
 
 def run_module(m, kind, case, device="cpu"):

@@ -15,6 +15,7 @@ from vidar_b200.modules import deform_attn
 from vidar_b200.registry import ATTENTION, build_attention
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "modules.npz")
+GOLD_CUSTOM = os.path.join(os.path.dirname(__file__), "golden", "modules_custom.npz")
 
 
 @pytest.fixture()
@@ -39,9 +40,24 @@ def test_module_matches_reference_class(oracle_msda, kind, cfg, case, seed):
     np.testing.assert_allclose(gkv[:, ::6].numpy(), g[f"{kind}_gkv_s6"], rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("kind,boxes,seed", [("custom", False, 13), ("custom_boxes", True, 14)])
+def test_detection_decoder_attention_matches_reference_class(oracle_msda, kind, boxes, seed):
+    """CustomMSDeformableAttention (decoder.py:132-345): sequence-first layout, both reference forms."""
+    g = np.load(GOLD_CUSTOM)
+    m = build_attention(mc.CUSTOM_CFG)
+    assert sorted(m.state_dict().keys()) == list(g[f"{kind}_params"])
+    assert m.batch_first is False
+    m.load_state_dict(mc.seeded_state(m, seed))
+    m.eval()
+    out, gq, gkv = mc.run_module(m, kind, mc.custom_case(boxes=boxes))
+    np.testing.assert_allclose(out.numpy(), g[f"{kind}_out"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(gq.numpy(), g[f"{kind}_gq"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(gkv.numpy(), g[f"{kind}_gkv"], rtol=1e-4, atol=2e-5)
+
+
 def test_registry_names_and_default_init():
     for name in ("SpatialCrossAttention", "MSDeformableAttention3D", "TemporalSelfAttention",
-                 "PredictionMSDeformableAttention"):
+                 "PredictionMSDeformableAttention", "CustomMSDeformableAttention"):
         assert name in ATTENTION
     m = build_attention(dict(type="MSDeformableAttention3D", embed_dims=256, num_points=8, num_levels=4))
     b = m.sampling_offsets.bias.view(8, 4, 8, 2)

@@ -12,6 +12,7 @@ from vidar_b200.registry import build_attention
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "modules.npz")
+GOLD_CUSTOM = os.path.join(os.path.dirname(__file__), "golden", "modules_custom.npz")
 
 
 @pytest.mark.parametrize("kind,cfg,case,seed", [("sca", mc.SCA_CFG, mc.sca_case, 10),
@@ -26,3 +27,15 @@ def test_module_on_gpu_matches_reference_class(cuda, kind, cfg, case, seed):
     np.testing.assert_allclose(out.cpu().numpy(), g[f"{kind}_out"], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(gq.cpu().numpy(), g[f"{kind}_gq"], rtol=1e-4, atol=5e-5)
     np.testing.assert_allclose(gkv[:, ::6].cpu().numpy(), g[f"{kind}_gkv_s6"], rtol=1e-4, atol=5e-5)
+
+
+@pytest.mark.parametrize("kind,boxes,seed", [("custom", False, 13), ("custom_boxes", True, 14)])
+def test_detection_decoder_attention_on_gpu(cuda, kind, boxes, seed):
+    g = np.load(GOLD_CUSTOM)
+    m = build_attention(mc.CUSTOM_CFG)
+    m.load_state_dict(mc.seeded_state(m, seed))
+    m.eval().to(cuda)
+    out, gq, gkv = mc.run_module(m, kind, mc.custom_case(boxes=boxes), device=cuda)
+    np.testing.assert_allclose(out.cpu().numpy(), g[f"{kind}_out"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(gq.cpu().numpy(), g[f"{kind}_gq"], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(gkv.cpu().numpy(), g[f"{kind}_gkv"], rtol=1e-4, atol=5e-5)

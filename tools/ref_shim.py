@@ -127,6 +127,13 @@ def install():
     for name in ("mmdet", "mmdet.models", "mmdet.models.utils", "mmdet3d", "mmdet3d.models",
                  "mmdet3d.models.losses"):
         mod(name, __path__=[])
+    # decoder.py imports plotting libraries it never uses on this path
+    for name in ("cv2", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except ImportError:
+                mod(name, __path__=[])
 
     pkg = types.ModuleType("vidar_ref")
     pkg.__path__ = [REF_BEVFORMER]

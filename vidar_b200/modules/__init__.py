@@ -1,3 +1,3 @@
-from .deform_attn import (MSDeformableAttention3D, PredictionMSDeformableAttention,  # noqa: F401
-                          SpatialCrossAttention, TemporalSelfAttention)
+from .deform_attn import (CustomMSDeformableAttention, MSDeformableAttention3D,  # noqa: F401
+                          PredictionMSDeformableAttention, SpatialCrossAttention, TemporalSelfAttention)
 from .latent_rendering import LatentRendering, latent_render_core  # noqa: F401

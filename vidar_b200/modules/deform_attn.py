@@ -8,6 +8,7 @@ classes, so the reference's config dicts build them and released checkpoints loa
   SpatialCrossAttention            spatial_cross_attention.py:30-174
   TemporalSelfAttention            temporal_self_attention.py:25-271
   PredictionMSDeformableAttention  vidar_decoder.py:289-516
+  CustomMSDeformableAttention      decoder.py:132-345   (detection decoder, fine-tuning only)
 (paths under projects/mmdet3d_plugin/bevformer/modules/ of the reference).
 
 Every sampling step goes through `msda_apply` = MultiScaleDeformableAttnFunction_fp32.apply,
@@ -345,3 +346,34 @@ class PredictionMSDeformableAttention(BaseModule):
         if not self.batch_first:
             output = output.permute(1, 0, 2)
         return self.dropout(output) + identity
+
+
+@ATTENTION.register_module()
+class CustomMSDeformableAttention(PredictionMSDeformableAttention):
+    """Deformable attention of the detection decoder (decoder.py:132-345): 900 object queries on
+    the single 200x200 BEV level.  Same parameters and arithmetic as the prediction variant; the
+    difference is the sequence-first default layout -- query `[num_query, bs, C]`, value
+    `[num_key, bs, C]` are permuted to batch-first before the projections (decoder.py:279-282) and
+    the output is permuted back (:340-343).  `identity` stays in the caller's layout."""
+
+    def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=4, im2col_step=64,
+                 dropout=0.1, batch_first=False, norm_cfg=None, init_cfg=None):
+        super().__init__(embed_dims, num_heads, num_levels, num_points, im2col_step, dropout,
+                         batch_first, norm_cfg, init_cfg)
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None,
+                key_padding_mask=None, reference_points=None, spatial_shapes=None,
+                level_start_index=None, flag="decoder", **kwargs):
+        if value is None:
+            value = query
+        if identity is None:
+            identity = query
+        if query_pos is not None:
+            query = query + query_pos
+            query_pos = None
+        if not self.batch_first:
+            query = query.permute(1, 0, 2)
+            value = value.permute(1, 0, 2)
+        # the parent adds `dropout(out) + identity` after permuting the output back
+        return super().forward(query, key, value, identity, query_pos, key_padding_mask, reference_points,
+                               spatial_shapes, level_start_index, flag, **kwargs)
