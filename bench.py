@@ -7,7 +7,7 @@ A "step" is one pass of ViDAR's two hot paths over one synthetic sample
        928x1600 input (30825 keys/cam), 200x200 = 40000 BEV queries per camera, 8 heads x 32
        channels, 8 sampling points per level (4 Z-anchors x 2);
   (ii) LatentRendering module forward + backward on a [1,200,200,256] BEV embedding
-       (pred_height 16, 256 waypoints of step 0.5, sigmoid; three Linear layers + fused core);
+       (pred_height 16, 256 waypoints of step 0.5, sigmoid; projections fused around the ray-marching core);
   (iii) ViDAR-head ray sampler + cross-entropy forward + backward: sigma [3,16,200,200], 30000
        LiDAR-like rays over 3 frames, 512 waypoints + the GT sample per ray;
   (iv) voxel ray-caster forward + loss backward (`dvr.render`, L2) on the same volume and rays.
@@ -430,9 +430,9 @@ def run_ours(args):
         "data": "synthetic (seeded: perspective pillar fan per camera, LiDAR-like rays)",
         "config": {"workload": WORKLOAD, "l2_policy": "inputs larger than L2 (1.4 GB of MSDA operands per step)",
                    "sharding": "rows of (camera,query) and rays split over ranks; local scatter-add into the BEV "
-                               "slots + all_reduce(BEV grid 41 MB), all_reduce(grad_sigma 7.7 MB); LatentRendering core: "
-                               "BEV cells split over ranks, all_reduce of the 2.56 MB maps between phases "
-                               "(its three Linear layers stay replicated)"
+                               "slots + all_reduce(BEV grid 41 MB), all_reduce(grad_sigma 7.7 MB); LatentRendering: BEV "
+                               "rows/cells split over ranks (projections and ray marching), all_reduce of the 2.56 MB "
+                               "maps between phases, all_gather of the 41 MB output / grad_embed rows"
                    if world > 1 else "single GPU"},
         "breakdown_ms": parts, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,

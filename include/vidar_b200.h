@@ -259,6 +259,31 @@ int vidar_latent_prob_backward(const float* occ, const float* aux, const float* 
                                float grid_step, int act, long long cell0, long long ncells,
                                void* stream);
 
+/* LatentRendering's projections around the ray-marching core, fused (one kernel per direction
+ * on each side; replaces 3 + 6 skinny cuBLAS GEMMs and the elementwise kernels between them):
+ *   latent_rendering.py:94   occ  = unsup_raymarching_head(embed)   (single Linear, num_pred_fcs == 0)
+ *   latent_rendering.py:134  feat = lora_a(embed)
+ *   latent_rendering.py:153-155  out = lora_b(pooled).view(.., D, E/D) * prob.view(.., D, 1)
+ * rows = bs*Hb*Wb (or any contiguous row range of it: pass offset pointers); E = embed_dims
+ * (128 or 256), D = pred_height, A = embed_dims / reduction; D + A <= 32.
+ * Weights in nn.Linear layout [out, in].  Backward entry points ADD into grad_w and grad_b
+ * (caller zero-fills) and overwrite the per-row gradients. */
+int vidar_latent_proj_in_forward(const float* embed, const float* w_occ, const float* b_occ,
+                                 const float* w_feat, const float* b_feat, float* occ, float* feat,
+                                 long long rows, int E, int D, int A, void* stream);
+int vidar_latent_proj_in_backward(const float* embed, const float* w_occ, const float* w_feat,
+                                  const float* grad_occ, const float* grad_feat, float* grad_embed,
+                                  float* grad_w_occ, float* grad_b_occ, float* grad_w_feat,
+                                  float* grad_b_feat, long long rows, int E, int D, int A,
+                                  void* stream);
+int vidar_latent_proj_out_forward(const float* pooled, const float* prob, const float* w,
+                                  const float* b, float* out, long long rows, int E, int D, int A,
+                                  void* stream);
+int vidar_latent_proj_out_backward(const float* grad_out, const float* pooled, const float* prob,
+                                   const float* w, const float* b, float* grad_pooled,
+                                   float* grad_prob, float* grad_w, float* grad_b,
+                                   long long rows, int E, int D, int A, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (i-b) BEV pillar -> camera projection, BEVFormerEncoder.point_sampling
  *   (projects/mmdet3d_plugin/bevformer/modules/encoder.py:94-156)

@@ -12,6 +12,7 @@ from vidar_b200.modules import latent_rendering as lr
 from vidar_b200.registry import build_attention
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "latent_rendering.npz")
+GOLD_FUSED = os.path.join(os.path.dirname(__file__), "golden", "latent_fused.npz")
 
 
 @pytest.fixture()
@@ -37,6 +38,34 @@ def test_module_with_oracle_core_matches_reference_class(oracle_core, tag, cfg, 
         key = f"{tag}_g_{n}"
         if key in g:
             np.testing.assert_allclose(p.grad.numpy(), g[key], rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,cfg,seed", [("fused", lc.CFG_FUSED, 23), ("fused_exp", lc.CFG_FUSED_EXP, 24)])
+def test_oracle_reproduces_goldens_of_the_fused_shapes(oracle_core, tag, cfg, seed):
+    """The goldens the fused-projection GPU path is held to (tests/test_latent_gpu.py), checked here
+    through the unfused host path + oracle core: outputs, grad embed and EVERY parameter gradient."""
+    g = np.load(GOLD_FUSED)
+    m = build_attention(cfg)
+    assert sorted(m.state_dict().keys()) == list(g[f"{tag}_params"])
+    assert lr.fused_projection_supported(m.embed_dims, m.pred_height, m.lora_a.out_features)
+    m.load_state_dict(lc.seeded_state(m, seed))
+    c = lc.case(seed=5, bev=lc.BEV_FUSED, embed_dims=cfg["embed_dims"])
+    e = c["embed"].clone().requires_grad_(True)
+    out = m(e)
+    out.backward(c["grad"])
+    np.testing.assert_allclose(out.detach().numpy(), g[f"{tag}_out"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(e.grad.numpy(), g[f"{tag}_gembed"], rtol=1e-3, atol=1e-6)
+    for n, p in m.named_parameters():
+        np.testing.assert_allclose(p.grad.numpy(), g[f"{tag}_g_{n}"], rtol=1e-3, atol=2e-6)
+
+
+def test_fused_projection_shape_gate():
+    ok = lr.fused_projection_supported
+    assert ok(256, 16, 16) and ok(128, 8, 16) and ok(256, 4, 16)
+    assert not ok(64, 16, 16)          # embed_dims not 128/256
+    assert not ok(256, 16, 32)         # rank != 16
+    assert not ok(256, 1, 16)          # 1 + 16 is not a multiple of 4 (class default pred_height)
+    assert not ok(256, 32, 16)         # rank not a multiple of pred_height
 
 
 def test_no_cpu_fallback():

@@ -40,3 +40,43 @@ def test_sharded_latent_core_equals_single_gpu(tmp_path):
     single, sharded = torch.load(out, weights_only=False)
     for a, b, w in zip(sharded, single, ["prob", "pooled", "grad_occ", "grad_feat"]):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()), msg=lambda m: f"{w}: {m}")
+
+
+def _module_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from tests import latent_cases as lc
+    import vidar_b200.modules  # noqa: F401
+    from vidar_b200.registry import build_attention
+    res = []
+    # 2 x 13 x 14 = 364 rows: an even split; 1 x 13 x 15 = 195 rows: uneven shards (97 + 98)
+    for bev, bs in (((13, 14), 2), ((13, 15), 1)):
+        m = build_attention(lc.CFG_FUSED)
+        m.load_state_dict(lc.seeded_state(m, 23))
+        m.cuda()
+        c = lc.case(seed=5, bs=bs, bev=bev, embed_dims=256)
+        for group in (None, dist.group.WORLD):
+            m.process_group = group
+            m.zero_grad(set_to_none=True)
+            e = c["embed"].cuda().requires_grad_(True)
+            o = m(e)
+            o.backward(c["grad"].cuda())
+            res.append([o.detach().cpu(), e.grad.cpu()] + [p.grad.cpu() for _, p in sorted(m.named_parameters())])
+    if rank == 0:
+        torch.save(res, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_fused_module_equals_single_gpu(tmp_path):
+    """The whole LatentRendering module (fused projections + core) with rows/cells split over two
+    GPUs returns the same replicated output, grad embed and parameter gradients as one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "m.pt")
+    mp.spawn(_module_worker, args=(2, 29440 + os.getpid() % 200, out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    for single, sharded in ((res[0], res[1]), (res[2], res[3])):
+        for i, (a, b) in enumerate(zip(sharded, single)):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5 * float(b.abs().max()), msg=lambda m: f"tensor {i}: {m}")

@@ -123,6 +123,24 @@ def main():
         out["latent_render_core_200x200x16_256wp_fwd_bwd_ms"]["torch_eager_reference_formula"] = f"failed: {e}"
     finally:
         torch.set_default_device("cpu")
+    # ---- LatentRendering MODULE (BASELINE configs[2]b): fused projections vs cuBLAS Linears around the same core
+    import vidar_b200.modules  # noqa: F401
+    from vidar_b200.registry import build_attention
+    torch.manual_seed(0)
+    mod = build_attention(bench.LR_CFG).to(dev)
+    emb = torch.randn(1, 200, 200, 256, device=dev, generator=g2)
+    gemb = torch.randn(1, 200, 200, 256, device=dev, generator=g2)
+
+    def module_step():
+        e = emb.detach().requires_grad_(True)
+        mod.zero_grad(set_to_none=True)
+        mod(e).backward(gemb)
+
+    rec = {}
+    for fused in (True, False):
+        mod.fuse_projections = fused
+        rec["fused_projections" if fused else "cublas_linears_around_core"] = timed(module_step, n=20)
+    out["latent_rendering_module_200x200x256_fwd_bwd_ms"] = rec
     print(json.dumps(out, indent=1))
 
 

@@ -35,7 +35,25 @@ def main():
             if n.startswith("lora_b.weight") or n.endswith("head.0.weight") or n.endswith("head.3.weight"):
                 rec[f"{tag}_g_{n}"] = p.grad.numpy()
         print(tag, tuple(out.shape), float(out.abs().mean()))
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "latent_rendering.npz"), **rec)
+    if "--fused-only" not in sys.argv:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "latent_rendering.npz"), **rec)
+    # shapes of the fused projection path: every parameter gradient is stored
+    rec = {}
+    for tag, cfg, seed in (("fused", lc.CFG_FUSED, 23), ("fused_exp", lc.CFG_FUSED_EXP, 24)):
+        kw = dict(cfg)
+        kw.pop("type")
+        m = mod.LatentRendering(**kw)
+        m.load_state_dict(lc.seeded_state(m, seed))
+        c = lc.case(seed=5, bev=lc.BEV_FUSED, embed_dims=cfg["embed_dims"])
+        e = c["embed"].clone().requires_grad_(True)
+        out = m(e)
+        out.backward(c["grad"])
+        rec[f"{tag}_out"], rec[f"{tag}_gembed"] = out.detach().numpy(), e.grad.numpy()
+        rec[f"{tag}_params"] = np.array(sorted(m.state_dict().keys()))
+        for n, p in m.named_parameters():
+            rec[f"{tag}_g_{n}"] = p.grad.numpy()
+        print(tag, tuple(out.shape), float(out.abs().mean()))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "latent_fused.npz"), **rec)
 
 
 if __name__ == "__main__":

@@ -6,10 +6,14 @@ projects/mmdet3d_plugin/bevformer/modules/ray_operations/latent_rendering.py:37-
 instantiated from the `latent_render=dict(...)` kwarg of the encoder/decoder layers
 (encoder_v2.py:81-82) and called as `latent_render(query.view(bs, bev_h, bev_w, C))`.
 
-The three Linear layers and the final product stay PyTorch ops (cuBLAS); the ray-marching
-between them -- grid_sample x3, masks, cumprod, normalisation, pooling in the reference -- is
-one custom autograd op (two kernels forward, two backward) that never materialises the
-[bs, 16, 40000, 257] tensors.  CUDA only.
+The ray-marching -- grid_sample x3, masks, cumprod, normalisation, pooling in the reference -- is
+a custom op (two kernels forward, two backward) that never materialises the [bs, 16, 40000, 257]
+tensors.  With the shipped configuration (`num_pred_fcs=0`, embed_dims 256, pred_height 16,
+reduction 16: vidar_1_8_nusc_3future.py:159-161) the three Linear layers and the final product
+are fused around it as well (csrc/latent_proj.cu): the whole module is six kernels forward+
+backward instead of ~35, and one autograd node (`_FusedLatentRendering`) that can shard the BEV
+cells over a process group.  Other configurations keep the Linear layers as PyTorch ops (cuBLAS)
+around the custom core.  CUDA only.
 """
 import torch
 import torch.nn as nn
@@ -133,6 +137,119 @@ class _ShardedLatentRenderCore(torch.autograd.Function):
         return grad_occ, gfe.clone() if both is not None else gfe, None, None, None, None, None
 
 
+def _group_world(group):
+    if group is None:
+        return 1
+    import torch.distributed as dist
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+class _FusedLatentRendering(torch.autograd.Function):
+    """The whole module as one node: embed [bs,Hb,Wb,E] + the six Linear parameters -> out.
+
+      forward : proj_in(rows) -> [all_reduce occ|feat] -> prob(cells) -> [all_reduce prob]
+                -> pool(cells) -> proj_out(rows) -> [all_gather out]
+      backward: proj_out_bwd(rows) -> pool_bwd(cells) -> [all_reduce grad_prob_map|grad_feat]
+                -> prob_bwd(cells) -> [all_reduce grad_occ] -> proj_in_bwd(rows)
+                -> [all_gather grad_embed, all_reduce parameter grads]
+    Bracketed steps only when `group` has more than one rank: every rank then owns a contiguous
+    share of the bs*Hb*Wb rows/cells; inputs, outputs and all returned gradients are
+    replicated, so the node is a drop-in for the single-GPU one."""
+
+    @staticmethod
+    def forward(ctx, embed, w_occ, b_occ, w_feat, b_feat, w_b, b_b, grid_num, grid_step, eps, act, group):
+        import torch.distributed as dist
+        from ..sharding import gather_rows, shard_range
+        _lib.require_cuda(embed=embed.contiguous())
+        params = [p.detach().float().contiguous() for p in (w_occ, b_occ, w_feat, b_feat, w_b, b_b)]
+        w_occ, b_occ, w_feat, b_feat, w_b, b_b = params
+        bs, Hb, Wb, E = embed.shape
+        D, A = w_occ.shape[0], w_feat.shape[0]
+        R = bs * Hb * Wb
+        x = embed.detach().float().contiguous().view(R, E)
+        world = _group_world(group)
+        c0, c1 = shard_range(R, dist.get_rank(group), world) if world > 1 else (0, R)
+        n = c1 - c0
+        dev = embed.device
+        alloc = torch.zeros if world > 1 else torch.empty
+        flat = alloc(R * (D + A), dtype=torch.float32, device=dev)       # occ | feat in one buffer: one collective
+        occ, feat = flat[: R * D].view(R, D), flat[R * D:].view(R, A)
+        prob = alloc((R, D), dtype=torch.float32, device=dev)
+        pooled = torch.empty((R, A), dtype=torch.float32, device=dev)    # only this rank's rows are filled / read
+        aux = torch.empty((3, R, D), dtype=torch.float32, device=dev)
+        out_l = torch.empty((n, E), dtype=torch.float32, device=dev)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(L.vidar_latent_proj_in_forward(_lib.ptr(x[c0:c1]), _lib.ptr(w_occ), _lib.ptr(b_occ), _lib.ptr(w_feat),
+                                                      _lib.ptr(b_feat), _lib.ptr(occ[c0:c1]), _lib.ptr(feat[c0:c1]), n, E, D, A, st))
+            if world > 1:
+                dist.all_reduce(flat, group=group)
+            _lib.check(L.vidar_latent_prob_forward(_lib.ptr(occ), _lib.ptr(prob), _lib.ptr(aux), bs, D, Hb, Wb,
+                                                   int(grid_num), float(grid_step), int(act), c0, n, st))
+            if world > 1:
+                dist.all_reduce(prob, group=group)
+            _lib.check(L.vidar_latent_pool_forward(_lib.ptr(prob), _lib.ptr(feat), _lib.ptr(pooled), _lib.ptr(aux), bs, D,
+                                                   A // D, Hb, Wb, int(grid_num), float(grid_step), float(eps), c0, n, st))
+            _lib.check(L.vidar_latent_proj_out_forward(_lib.ptr(pooled[c0:c1]), _lib.ptr(prob[c0:c1]), _lib.ptr(w_b),
+                                                       _lib.ptr(b_b), _lib.ptr(out_l), n, E, D, A, st))
+            out = gather_rows(out_l, world, R, group)
+        ctx.save_for_backward(x, occ, feat, prob, pooled, aux, *params)
+        ctx.cfg = (int(grid_num), float(grid_step), float(eps), int(act), group, world, c0, n, (bs, Hb, Wb, E, D, A))
+        return out.view(bs, Hb, Wb, E)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        import torch.distributed as dist
+        from ..sharding import gather_rows
+        x, occ, feat, prob, pooled, aux, w_occ, b_occ, w_feat, b_feat, w_b, b_b = ctx.saved_tensors
+        grid_num, grid_step, eps, act, group, world, c0, n, (bs, Hb, Wb, E, D, A) = ctx.cfg
+        R, c1 = bs * Hb * Wb, c0 + n
+        dev = x.device
+        g = grad_out.float().contiguous().view(R, E)
+        # parameter gradients in one buffer (one all-reduce when sharded): w_occ b_occ w_feat b_feat w_b b_b
+        sizes = [D * E, D, A * E, A, E * A, E]
+        pg = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        g_w_occ, g_b_occ, g_w_feat, g_b_feat, g_w_b, g_b_b = torch.split(pg, sizes)
+        g_pooled = torch.empty((R, A), dtype=torch.float32, device=dev)       # rows [c0, c1) used
+        g_prob = torch.empty((n, D), dtype=torch.float32, device=dev)
+        maps = torch.zeros(R * (D + A), dtype=torch.float32, device=dev)      # grad_prob_map | grad_feat
+        gpm, gfe = maps[: R * D].view(R, D), maps[R * D:].view(R, A)
+        grad_occ = torch.zeros((R, D), dtype=torch.float32, device=dev)
+        gx_l = torch.empty((n, E), dtype=torch.float32, device=dev)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(L.vidar_latent_proj_out_backward(_lib.ptr(g[c0:c1]), _lib.ptr(pooled[c0:c1]), _lib.ptr(prob[c0:c1]),
+                                                        _lib.ptr(w_b), _lib.ptr(b_b), _lib.ptr(g_pooled[c0:c1]), _lib.ptr(g_prob),
+                                                        _lib.ptr(g_w_b), _lib.ptr(g_b_b), n, E, D, A, st))
+            _lib.check(L.vidar_latent_pool_backward(_lib.ptr(prob), _lib.ptr(feat), _lib.ptr(pooled), _lib.ptr(aux),
+                                                    _lib.ptr(g_pooled), _lib.ptr(gpm), _lib.ptr(gfe), bs, D, A // D,
+                                                    Hb, Wb, grid_num, grid_step, eps, c0, n, st))
+            if world > 1:
+                dist.all_reduce(maps, group=group)
+            gpm[c0:c1] += g_prob          # prob's direct use in the final product (this rank's cells)
+            _lib.check(L.vidar_latent_prob_backward(_lib.ptr(occ), _lib.ptr(aux), _lib.ptr(gpm), _lib.ptr(grad_occ), bs, D,
+                                                    Hb, Wb, grid_num, grid_step, act, c0, n, st))
+            if world > 1:
+                dist.all_reduce(grad_occ, group=group)
+            _lib.check(L.vidar_latent_proj_in_backward(_lib.ptr(x[c0:c1]), _lib.ptr(w_occ), _lib.ptr(w_feat),
+                                                       _lib.ptr(grad_occ[c0:c1]), _lib.ptr(gfe[c0:c1]), _lib.ptr(gx_l),
+                                                       _lib.ptr(g_w_occ), _lib.ptr(g_b_occ), _lib.ptr(g_w_feat),
+                                                       _lib.ptr(g_b_feat), n, E, D, A, st))
+            if world > 1:
+                dist.all_reduce(pg, group=group)
+            gx = gather_rows(gx_l, world, R, group)
+        return (gx.view(bs, Hb, Wb, E), g_w_occ.view(D, E), g_b_occ, g_w_feat.view(A, E), g_b_feat, g_w_b.view(E, A), g_b_b,
+                None, None, None, None, None)
+
+
+def fused_projection_supported(E, D, A):
+    """Shapes csrc/latent_proj.cu handles (the shipped configuration is E=256, D=16, A=16)."""
+    return (E in (128, 256) and A == 16 and A % D == 0 and (D + A) % 4 == 0 and D + A <= 32
+            and E % D == 0 and (E // D) % 4 == 0 and 128 % (E // D) == 0)
+
+
 def latent_render_core(occ, feat, grid_num, grid_step, eps, act, group=None):
     """(occ, feat) -> (prob, pooled).  `group`: a torch.distributed process group over which the BEV
     cells are sharded (None or a 1-rank group = single GPU)."""
@@ -167,13 +284,22 @@ class LatentRendering(BaseModule):
         self.lora_a = nn.Linear(self.embed_dims, self.embed_dims // reduction)
         self.lora_b = nn.Linear(self.embed_dims // reduction, self.embed_dims)
         self.process_group = None     # set to a process group to shard the BEV cells over its ranks
+        self.fuse_projections = True  # False: keep the Linear layers as PyTorch ops around the CUDA core
 
     def forward(self, embed, eps=1e-3, **kwargs):
         """embed [bs, bev_h, bev_w, embed_dims] -> same shape."""
         if self.act not in _ACT:
             raise NotImplementedError("Only support exp or sigmoid activation_fn for now.")
         bs, bev_h, bev_w, _ = embed.shape
-        occ = self.unsup_raymarching_head(embed)            # [bs, h, w, pred_height]   (:94)
+        head = self.unsup_raymarching_head
+        if (self.fuse_projections and len(head) == 1 and embed.is_cuda and embed.dtype == torch.float32
+                and not torch.is_autocast_enabled()
+                and fused_projection_supported(self.embed_dims, self.pred_height, self.lora_a.out_features)
+                and all(p is not None for p in (head[0].bias, self.lora_a.bias, self.lora_b.bias))):
+            return _FusedLatentRendering.apply(embed, head[0].weight, head[0].bias, self.lora_a.weight, self.lora_a.bias,
+                                               self.lora_b.weight, self.lora_b.bias, self.grid_num, self.grid_step, eps,
+                                               _ACT[self.act], self.process_group)
+        occ = head(embed)                                   # [bs, h, w, pred_height]   (:94)
         feat = self.lora_a(embed)                           # [bs, h, w, embed/reduction] (:134)
         prob, pooled = latent_render_core(occ, feat, self.grid_num, self.grid_step, eps, _ACT[self.act],
                                           self.process_group)

@@ -45,15 +45,19 @@ def camera_groups(world, cams, Q, rank):
     return groups
 
 
-def gather_rows(local_rows, world, total_rows):
+def gather_rows(local_rows, world, total_rows, group=None):
     """all-gather of per-rank row blocks [n_r, C] (balanced contiguous shards) -> [total_rows, C]."""
     if world == 1:
         return local_rows
+    if total_rows % world == 0:
+        full = local_rows.new_empty(total_rows, local_rows.shape[1])
+        dist.all_gather_into_tensor(full.view(-1), local_rows.contiguous().view(-1), group=group)
+        return full
     max_rows = -(-total_rows // world)
     pad = local_rows.new_zeros(max_rows, local_rows.shape[1])
     pad[: local_rows.shape[0]] = local_rows
     flat = local_rows.new_empty(world * max_rows, local_rows.shape[1])
-    dist.all_gather_into_tensor(flat, pad)
+    dist.all_gather_into_tensor(flat.view(-1), pad.view(-1), group=group)
     buf = flat.view(world, max_rows, local_rows.shape[1])
     parts = []
     for r in range(world):
