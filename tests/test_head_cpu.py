@@ -1,0 +1,65 @@
+"""Host logic of the ViDAR head mirror (vidar_b200/head.py) that needs no GPU, against goldens from
+the REFERENCE methods (tools/make_golden_head.py)."""
+import os
+
+import numpy as np
+import torch
+
+from tests import head_cases as hc
+from vidar_b200.head import ViDARRayHead, get_inside_mask
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "head.npz")
+
+
+def _head():
+    c = hc.case()
+    return ViDARRayHead(loss_weight=c["loss_weight"], **hc.HEAD_KW), c
+
+
+def test_process_gt_points_matches_reference():
+    g = np.load(GOLD)
+    head, c = _head()
+    preds = c["pred_dict"]["next_bev_preds"][:, -1:]
+    og, op, gg, gp, gt = head._process_gt_points(preds, c["gt_points"], c["origin"], [0, 1], 0, hc.FRAMES, hc.BEV_H,
+                                                 hc.BEV_W, hc.PC_RANGE)
+    np.testing.assert_array_equal(og.numpy(), g["origin_grids"])
+    np.testing.assert_array_equal(gg.numpy(), g["gt_grids"])          # NaN padding compares equal
+    np.testing.assert_array_equal(gp.numpy(), g["gt_points"])
+    np.testing.assert_array_equal(gt.numpy(), g["gt_tindex"])
+    assert (gt == -1).any() and gt.max() == hc.FRAMES - 1
+    # origin defaults to the ego position (zeros) when not given
+    og0, op0, *_ = head._process_gt_points(preds, c["gt_points"], None, [0, 1], 0, hc.FRAMES, hc.BEV_H, hc.BEV_W, hc.PC_RANGE)
+    assert float(op0.abs().sum()) == 0 and torch.allclose(og0[0, 0], torch.tensor([hc.BEV_W / 2, hc.BEV_H / 2, hc.Z / 2]))
+
+
+def test_gumbel_distance_with_given_noise_equals_torch_draw():
+    head, _ = _head()
+    g = torch.Generator().manual_seed(3)
+    embed = torch.randn(2, 17, 20, generator=g).requires_grad_(True)
+    length = (torch.arange(20.0) + 0.5).expand(2, 17, 20)
+    torch.manual_seed(5)
+    a = head._custom_gumbel_softmax_distance(embed, length)
+    torch.manual_seed(5)
+    noise = -torch.empty_like(embed).exponential_().log()
+    b = head._custom_gumbel_softmax_distance(embed, length, noise)
+    assert torch.equal(a, b)
+    # value = sampled waypoint length, gradient flows only through the "mass beyond it" term
+    assert set(np.unique(a.detach().numpy())) <= set(np.unique(length.numpy()))
+    (ga,) = torch.autograd.grad(a.sum(), embed)
+    assert torch.isfinite(ga).all() and float(ga.abs().sum()) > 0
+
+
+def test_rendered_pcds_and_inside_mask():
+    head, _ = _head()
+    origin = torch.tensor([[[0.0, 0.0, 0.0], [1.0, 0.0, 0.0]]])
+    pts = torch.tensor([[[2.0, 0.0, 0.0], [0.0, 3.0, 0.0], [1.0, 0.0, 4.0], [9.0, 9.0, 9.0]]])
+    tindex = torch.tensor([[0.0, 0.0, 1.0, -1.0]])
+    gt_dist = torch.tensor([[2.0, 0.0, 4.0, 1.0]])                   # second ray masked by gt_dist == 0
+    pred = torch.tensor([[1.0, 5.0, 2.0, 7.0]])
+    pcds = head.get_rendered_pcds(origin, pts, tindex, gt_dist, pred, hc.PC_RANGE)
+    assert torch.allclose(pcds[0][0], torch.tensor([[1.0, 0.0, 0.0]]))
+    assert torch.allclose(pcds[0][1], torch.tensor([[1.0, 0.0, 2.0]]))
+    head.eval_within_grid = True
+    pcds = head.get_rendered_pcds(origin, pts, tindex, gt_dist, pred, [-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
+    assert pcds[0][0].shape[0] == 0 and pcds[0][1].shape[0] == 0     # both GT points lie outside that box
+    assert get_inside_mask(pts[0], hc.PC_RANGE).tolist() == [True, True, False, False]

@@ -156,6 +156,39 @@ def install():
     return pkg
 
 
+def load_functions(relpath, names):
+    """Execute ONLY the named top-level functions of a reference file (plus its plain imports that
+    resolve here) and return them as a dict -- for files whose module body cannot run in this
+    container (e2e_predictor_utils.py JIT-compiles CUDA extensions at import).  The source is read
+    from /root/reference at call time; nothing is copied into the repo."""
+    import ast
+    path = os.path.join(REF_BEVFORMER, relpath)
+    with open(path) as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    ns = {"__name__": "vidar_ref._functions"}
+    for node in tree.body:
+        if isinstance(node, (ast.Import, ast.ImportFrom)) and not getattr(node, "level", 0):
+            try:
+                exec(compile(ast.Module([node], []), path, "exec"), ns)
+            except ImportError:
+                pass
+        elif isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return {n: ns[n] for n in names}
+
+
+def install_e2e_utils():
+    """Put the pure helpers of utils/e2e_predictor_utils.py on the stub module the heads import."""
+    install()
+    stub = sys.modules["vidar_ref.utils.e2e_predictor_utils"]
+    fns = load_functions(os.path.join("utils", "e2e_predictor_utils.py"),
+                         ("coords_to_voxel_grids", "get_bev_grids", "get_bev_grids_3d", "get_inside_mask"))
+    for k, v in fns.items():
+        setattr(stub, k, v)
+    sys.modules["vidar_ref.utils"].e2e_predictor_utils = stub      # `from ..utils import e2e_predictor_utils`
+    return stub
+
+
 def load(dotted):
     """e.g. load('modules.spatial_cross_attention') -> module object of the reference file."""
     install()
