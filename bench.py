@@ -305,6 +305,12 @@ def run_ours(args):
     parts = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, n in enumerate(names)}
 
     if os.environ.get("VIDAR_BENCH_PROFILE") == "1":   # under ncu: kernels only
+        # one more step inside a cudaProfilerStart/Stop range: `ncu --profile-from-start off`
+        # captures exactly this step's kernels (tools/profile_round.sh)
+        torch.cuda.profiler.start()
+        step(False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         if rank == 0:
             _emit(json.dumps({"profile_only": True, "ms_per_step": ms_step, "breakdown_ms": parts}))
         return

@@ -33,34 +33,52 @@ KEEP = [
 
 
 def raw(rep):
+    """-> (header, units, [one row per DISTINCT kernel in the report, first launch of each])."""
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    return rows[0], rows[1], rows[2]
+    hdr = rows[0]
+    ki = hdr.index("Kernel Name") if "Kernel Name" in hdr else None
+    seen, keep = set(), []
+    for r in rows[2:]:
+        key = r[ki] if ki is not None else len(keep)
+        if key not in seen:
+            seen.add(key)
+            keep.append(r)
+    return hdr, rows[1], keep
+
+
+def short_name(kernel):
+    """vidar::<unnamed>::msda_backward_kernel<8, 0>(...) -> msda_backward"""
+    k = kernel.split("(")[0].split("::")[-1]
+    k = k.split("<")[0]
+    return k[:-7] if k.endswith("_kernel") else k
 
 
 def main():
     os.makedirs(DST, exist_ok=True)
     traffic = {}
-    lines = [f"# ncu --set full --clock-control none, one launch each, bench.py --steps 2 --warmup 3 ({TAG})", ""]
+    lines = [f"# ncu --set full --clock-control none, first launch of each kernel in one bench.py step ({TAG}; tools/profile_round.sh)", ""]
     for f in sorted(os.listdir(SRC)):
         if not (f.startswith(TAG + "_") and f.endswith(".ncu-rep")):
             continue
-        hdr, units, vals = raw(os.path.join(SRC, f))
-        name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else f
-        lines.append(f"## {f[len(TAG) + 1:-8]}  ({name[:90]})")
-        rec = {}
-        for k in KEEP:
-            if k in hdr:
-                i = hdr.index(k)
-                lines.append(f"  {k:88s} {vals[i]:>16s} {units[i]}")
-                rec[k] = (vals[i], units[i])
-        lines.append("")
+        hdr, units, kernels = raw(os.path.join(SRC, f))
+        for vals in kernels:
+            name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else f
+            section = f[len(TAG) + 1:-8] if len(kernels) == 1 else short_name(name)
+            lines.append(f"## {section}  ({name[:90]})")
+            rec = {}
+            for k in KEEP:
+                if k in hdr:
+                    i = hdr.index(k)
+                    lines.append(f"  {k:88s} {vals[i]:>16s} {units[i]}")
+                    rec[k] = (vals[i], units[i])
+            lines.append("")
 
-        def to_bytes(key):
-            v, u = rec.get(key, ("0", "byte"))
-            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-            return float(v.replace(",", "")) * mult
-        traffic[f[len(TAG) + 1:-8]] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+            def to_bytes(key):
+                v, u = rec.get(key, ("0", "byte"))
+                mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+                return float(v.replace(",", "")) * mult
+            traffic[section] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
     with open(os.path.join(DST, f"{TAG}_ncu_summary.txt"), "w") as fh:
         fh.write("\n".join(lines))
     # launch list -> per-kernel totals and shares
@@ -82,6 +100,7 @@ def main():
                 fh.write(f"{sum(v) / tot * 100:6.2f}%  n={len(v):4d}  total={sum(v) / 1e6:9.3f} ms  avg={sum(v) / len(v) / 1e3:9.1f} us  {k[:110]}\n")
     with open(os.path.join(DST, "roofline_traffic.json"), "w") as fh:
         json.dump({"msda_bwd": traffic.get("msda_backward"), "msda_fwd": traffic.get("msda_forward"),
+                   "tag": TAG,
                    "all_dram_bytes_per_launch": traffic, "source": f"profiles/{TAG}_ncu_summary.txt"}, fh, indent=1)
     print(open(os.path.join(DST, f"{TAG}_launches_summary.txt")).read()[:1800])
 
