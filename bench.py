@@ -222,6 +222,7 @@ def run_ours(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     names = ["msda_fwd", "msda_bwd", "latent_render", "ray_ce", "render"]
+    ray_grads = torch.empty((2,) + tuple(sigma.shape[1:]), device=dev) if world > 1 else None
     marks = []
 
     def step(record):
@@ -261,17 +262,20 @@ def run_ours(args):
         sg = sigma[0].detach().requires_grad_(True)
         ce, valid = ray_head.ray_ce(sg, ce_origin, ce_points, ce_frame, WAYPOINTS, 1.0)
         ce.sum().backward()
-        if world > 1:
-            dist.all_reduce(sg.grad)
         if record:
             e[4].record()
         pred, gt, grad_sigma = render.dvr.render(sigma, origin, points, tindex, "l2")
+        ce_grad = sg.grad
         if world > 1:
-            dist.all_reduce(grad_sigma)
+            # the two ray stages' partial sigma gradients (7.7 MB each) travel in ONE all-reduce
+            ray_grads[0].copy_(ce_grad)
+            ray_grads[1].copy_(grad_sigma[0])
+            dist.all_reduce(ray_grads)
+            ce_grad, grad_sigma = ray_grads[0], ray_grads[1][None]
         if record:
             e[5].record()
             marks.append(e)
-        return outs, grads, pred, grad_sigma, emb.grad, sg.grad
+        return outs, grads, pred, grad_sigma, emb.grad, ce_grad
 
     def sync():
         torch.cuda.synchronize()
@@ -436,7 +440,7 @@ def run_ours(args):
         "data": "synthetic (seeded: perspective pillar fan per camera, LiDAR-like rays)",
         "config": {"workload": WORKLOAD, "l2_policy": "inputs larger than L2 (1.4 GB of MSDA operands per step)",
                    "sharding": "rows of (camera,query) and rays split over ranks; local scatter-add into the BEV "
-                               "slots + all_reduce(BEV grid 41 MB), all_reduce(grad_sigma 7.7 MB); LatentRendering: BEV "
+                               "slots + all_reduce(BEV grid 41 MB), one all_reduce of both ray stages' grad_sigma (2 x 7.7 MB); LatentRendering: BEV "
                                "rows/cells split over ranks (projections and ray marching), all_reduce of the 2.56 MB "
                                "maps between phases, all_gather of the 41 MB output / grad_embed rows"
                    if world > 1 else "single GPU"},
