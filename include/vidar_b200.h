@@ -81,6 +81,26 @@ int vidar_msda_backward(const float* value, const int64_t* spatial_shapes,
                         int B, int K, int H, int C, int L, int Q, int P,
                         int im2col_step, void* stream);
 
+/* MSDeformableAttention3D's sampling with its elementwise prologue folded in
+ *   (spatial_cross_attention.py:339-371 + the two calls above):
+ *     attn = softmax_{L*P}(logits)                       (:339-342)
+ *     loc  = offsets / (W_l, H_l) + ref_points[b, q, p % D]   (:356-371, point p = j*D + z)
+ *   ref_points  [B, Q, D, 2]        projected Z-anchors (reference_points_cam), normalised
+ *   offsets     [B, Q, H, L, P, 2]  raw output of the sampling_offsets Linear (pixels of level l)
+ *   logits      [B, Q, H, L*P]      raw output of the attention_weights Linear
+ * Requires L*P == 32 and head dim 16/32/64 (the shipped SCA configuration: 4 levels x 8 points).
+ * Backward: grad_value accumulated (caller zeroes), grad_offsets / grad_logits overwritten; the
+ * reference points carry no gradient (they come from the camera geometry). */
+int vidar_msda_sca_forward(const float* value, const int64_t* spatial_shapes,
+                           const int64_t* level_start, const float* ref_points,
+                           const float* offsets, const float* logits, float* out,
+                           int B, int K, int H, int C, int L, int Q, int P, int D, void* stream);
+int vidar_msda_sca_backward(const float* value, const int64_t* spatial_shapes,
+                            const int64_t* level_start, const float* ref_points,
+                            const float* offsets, const float* logits, const float* grad_out,
+                            float* grad_value, float* grad_offsets, float* grad_logits,
+                            int B, int K, int H, int C, int L, int Q, int P, int D, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (ii-a) dvr / dvxlr / dvxlr_v2 voxel ray-casters
  *   sigma   [N, T, Z, Y, X]   (reference names the dims H, L, W)

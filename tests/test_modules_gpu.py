@@ -39,3 +39,23 @@ def test_detection_decoder_attention_on_gpu(cuda, kind, boxes, seed):
     np.testing.assert_allclose(out.cpu().numpy(), g[f"{kind}_out"], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(gq.cpu().numpy(), g[f"{kind}_gq"], rtol=1e-4, atol=5e-5)
     np.testing.assert_allclose(gkv.cpu().numpy(), g[f"{kind}_gkv"], rtol=1e-4, atol=5e-5)
+
+
+def test_sca_fused_epilogue_equals_materialised_path(cuda):
+    """SpatialCrossAttention through MSDeformableAttention3D with the softmax / sampling-location
+    arithmetic inside the kernel (default) vs materialised `sampling_locations` / `attention_weights`."""
+    m = build_attention(mc.SCA_CFG)
+    m.load_state_dict(mc.seeded_state(m, 10))
+    m.eval().to(cuda)
+    assert m.deformable_attention.fuse_epilogue
+    res = []
+    for fused in (True, False):
+        m.deformable_attention.fuse_epilogue = fused
+        m.zero_grad(set_to_none=True)
+        out, gq, gkv = mc.run_module(m, "sca", mc.sca_case(), device=cuda)
+        res.append((out, gq, gkv, m.deformable_attention.sampling_offsets.weight.grad.clone(),
+                    m.deformable_attention.attention_weights.weight.grad.clone()))
+    for a, b, w in zip(res[0], res[1], ("out", "grad query", "grad key/value", "grad sampling_offsets.weight",
+                                        "grad attention_weights.weight")):
+        err = (a - b).abs().max().item()
+        assert err <= 2e-5 * b.abs().max().item() + 1e-7, f"{w}: {err:.3e} vs {b.abs().max().item():.3e}"

@@ -176,3 +176,50 @@ def test_edge_inputs(cuda):
     ga = torch.full_like(attn, 5.0)
     msda.ext_module.ms_deform_attn_backward(value, shapes, lsi, loc, attn, torch.ones(2, 9, 256, device=cuda), gv, gl, ga, im2col_step=64)
     assert float(gl[0, :3].abs().max()) == 0 and float(ga[1, 4:].abs().max()) == 0 and torch.isfinite(gv).all()
+
+
+@pytest.mark.parametrize("C,levels,P,D", [(32, SCA_LEVELS, 8, 4), (16, ((20, 30), (10, 15)), 16, 2), (64, ((9, 7),), 32, 8)])
+def test_fused_sca_epilogue_equals_materialised_path(cuda, C, levels, P, D):
+    """vidar_msda_sca_*: softmax + `offsets / (W,H) + ref[p % D]` inside the kernel vs the reference's
+    statements (spatial_cross_attention.py:339-371) in torch followed by the plain op.  The location
+    arithmetic is bit-identical (same IEEE divide + add), the softmax differs by summation order."""
+    B, Q, H = 2, 300, 8
+    L = len(levels)
+    shapes, lsi = level_tensors(levels)
+    K = int((shapes[:, 0] * shapes[:, 1]).sum())
+    g = torch.Generator().manual_seed(C + P)
+    value = torch.randn(B, K, H, C, generator=g).to(cuda)
+    ref = (torch.rand(B, Q, D, 2, generator=g) * 1.2 - 0.1).to(cuda)              # some anchors outside the image
+    offsets = (3.0 * torch.randn(B, Q, H, L, P, 2, generator=g)).to(cuda)
+    logits = (2.0 * torch.randn(B, Q, H, L * P, generator=g)).to(cuda)
+    grad = torch.randn(B, Q, H * C, generator=g).to(cuda)
+    shapes, lsi = shapes.to(cuda), lsi.to(cuda)
+
+    v1, o1, l1 = (t.clone().requires_grad_(True) for t in (value, offsets, logits))
+    out1 = msda.MSDeformAttn3DFusedFunction.apply(v1, shapes, lsi, ref, o1, l1)
+    out1.backward(grad)
+
+    v2, o2, l2 = (t.clone().requires_grad_(True) for t in (value, offsets, logits))
+    wh = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+    off = o2 / wh[None, None, None, :, None, :]
+    loc = (off.view(B, Q, H, L, P // D, D, 2) + ref[:, :, None, None, None, :, :]).view(B, Q, H, L, P, 2)
+    w = l2.softmax(-1).view(B, Q, H, L, P)
+    out2 = msda.MultiScaleDeformableAttnFunction_fp32.apply(v2, shapes, lsi, loc, w, 64)
+    out2.backward(grad)
+
+    _close(out1, out2, "out")
+    _close(v1.grad, v2.grad, "grad_value")
+    _close(l1.grad, l2.grad, "grad_logits")
+    # grad wrt offsets inherits grad_loc's pixel-centre discontinuities: exclude samples near a kink
+    keep = _off_kink(dict(loc=loc.detach().cpu(), shapes=shapes.cpu()))
+    _close(o1.grad, o2.grad, "grad_offsets", keep=keep[..., None].expand(-1, -1, -1, -1, -1, 2))
+    assert msda.MSDeformAttn3DFusedFunction.supported(L, P, C, D)
+    assert not msda.MSDeformAttn3DFusedFunction.supported(4, 4, 32, 4)
+
+
+def test_fused_sca_epilogue_rejects_other_shapes(cuda):
+    shapes, lsi = level_tensors(((8, 8),))
+    v = torch.zeros(1, 64, 8, 32, device=cuda)
+    with pytest.raises(RuntimeError, match="num_levels \\* num_points == 32"):
+        msda.MSDeformAttn3DFusedFunction.apply(v, shapes.to(cuda), lsi.to(cuda), torch.zeros(1, 5, 4, 2, device=cuda),
+                                               torch.zeros(1, 5, 8, 1, 4, 2, device=cuda), torch.zeros(1, 5, 8, 4, device=cuda))

@@ -141,6 +141,29 @@ def main():
         mod.fuse_projections = fused
         rec["fused_projections" if fused else "cublas_linears_around_core"] = timed(module_step, n=20)
     out["latent_rendering_module_200x200x256_fwd_bwd_ms"] = rec
+    # ---- MSDeformableAttention3D module (the per-camera attention of SCA), 6 cameras x 10000 visible pillars:
+    #      softmax / sampling-location arithmetic inside the kernel vs materialised like the reference
+    att = build_attention(dict(type="MSDeformableAttention3D", embed_dims=256, num_points=8, num_levels=4)).to(dev)
+    att.sampling_offsets.weight.data.normal_(0, 0.02)
+    att.attention_weights.weight.data.normal_(0, 0.02)
+    shapes3 = torch.tensor(bench.LEVELS, dtype=torch.int64, device=dev)
+    lsi3 = torch.cat([shapes3.new_zeros(1), (shapes3[:, 0] * shapes3[:, 1]).cumsum(0)[:-1]])
+    K3 = int((shapes3[:, 0] * shapes3[:, 1]).sum())
+    q3 = torch.randn(6, 10000, 256, device=dev, generator=g2)
+    v3 = torch.randn(6, K3, 256, device=dev, generator=g2)
+    r3 = torch.rand(6, 10000, 4, 2, device=dev, generator=g2)
+    go3 = torch.randn(6, 10000, 256, device=dev, generator=g2)
+
+    def att_step():
+        qq, vv = q3.detach().requires_grad_(True), v3.detach().requires_grad_(True)
+        att.zero_grad(set_to_none=True)
+        att(qq, vv, vv, reference_points=r3, spatial_shapes=shapes3, level_start_index=lsi3).backward(go3)
+
+    rec = {}
+    for fused in (True, False):
+        att.fuse_epilogue = fused
+        rec["fused_epilogue" if fused else "materialised_loc_and_weights"] = timed(att_step, n=10)
+    out["msdeformattn3d_module_6cams_10000q_fwd_bwd_ms"] = rec
     print(json.dumps(out, indent=1))
 
 

@@ -39,6 +39,10 @@ struct MsdaParams {
   int lp_shift;       // log2(LP) when ipw > 1
   int pix_stride;     // H*C floats between neighbouring pixels
   long long items;    // B*Q*H
+  // fused sampling-location / softmax epilogue (EPI kernels): `loc` then holds the raw offsets
+  // of the sampling_offsets Linear, `attn` the logits of the attention_weights Linear
+  const float* ref;   // [B, Q, D, 2] projected Z-anchors (reference_points_cam), normalised
+  int D;
 };
 
 // Decode one sample: pixel coordinates -> clamped base pixel, corner mask, fractions.
@@ -111,6 +115,35 @@ __device__ __forceinline__ float4 f4_scale(float s, const float4& v) {
   return r;
 }
 
+
+// EPI (MSDeformableAttention3D, spatial_cross_attention.py:339-371 folded into the kernel): lane s
+// holds sample s = l*P + p of one (b,q,h); the attention weight is the softmax of the 32 logits
+// (`attention_weights.softmax(-1)`, :342) and the location is
+//   loc = offsets / (W_l, H_l) + reference_points_cam[b, q, p % D]      (:356-371)
+// with the reference's operation order (a true division, then an add; no FMA contraction).
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void epi_decode(const MsdaParams& p, long long item0, int s, float Wl, float Hl,
+                                           const float* loc0, const float* att0, float2& xy, float& aw) {
+  const float logit = __ldg(att0 + s);
+  const float e = expf(logit - warp_max(logit));
+  aw = __fdiv_rn(e, warp_sum(e));
+  const float2 off = __ldg(reinterpret_cast<const float2*>(loc0) + s);
+  const long long bq = item0 / p.H;
+  const int z = (s % p.P) % p.D;
+  const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) + bq * p.D + z);
+  xy.x = __fadd_rn(__fdiv_rn(off.x, Wl), r.x);
+  xy.y = __fadd_rn(__fdiv_rn(off.y, Hl), r.y);
+}
+
 // Which (b,q,h) items does this warp own?  Returns false if none.
 //  ipw == 1 : block = 8 consecutive queries of one (b,h); blocks ordered (b, h, qtile).
 //  ipw  > 1 : ipw consecutive items in memory order (heads of the same query first).
@@ -160,7 +193,8 @@ __device__ __forceinline__ void store_item(const MsdaParams& p, float* __restric
 }
 
 // MULTI = several items per warp (L*P a power of two < 32, one 32-sample chunk).
-template <int CV, bool MULTI>
+// EPI = fused softmax / sampling-location epilogue (L*P == 32, !MULTI only).
+template <int CV, bool MULTI, bool EPI = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
   constexpr int NG = 32 / CV;       // sample groups per warp
@@ -186,11 +220,17 @@ msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
     float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
     const bool live = MULTI ? (item0 + (s >> p.lp_shift) < p.items) : (s < span);
     if (live) {
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc0) + s);
-      const float aw = __ldg(att0 + s);
       const int sl = MULTI ? (s & (p.LP - 1)) : s;
       const int l = sl / p.P;
       const int Hl = (int)__ldg(p.shapes + 2 * l), Wl = (int)__ldg(p.shapes + 2 * l + 1);
+      float2 xy;
+      float aw;
+      if (EPI) {            // all 32 lanes are live here (L*P == 32)
+        epi_decode(p, item0, s, (float)Wl, (float)Hl, loc0, att0, xy, aw);
+      } else {
+        xy = __ldg(reinterpret_cast<const float2*>(loc0) + s);
+        aw = __ldg(att0 + s);
+      }
       float lh, lw;
       decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw, p.pix_stride);
       const float hh = 1.f - lh, hw = 1.f - lw;
@@ -239,7 +279,7 @@ msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
   store_item<CV>(p, out, MULTI ? item0 + p.ipw - 1 : item0, acc, g, cl);
 }
 
-template <int CV, bool MULTI>
+template <int CV, bool MULTI, bool EPI = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
                      float* __restrict__ grad_value, float* __restrict__ grad_loc,
@@ -270,11 +310,16 @@ msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
     float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
     const bool live = MULTI ? (item0 + (s >> p.lp_shift) < p.items) : (s < span);
     if (live) {
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc0) + s);
-      aw = __ldg(att0 + s);
       const int sl = MULTI ? (s & (p.LP - 1)) : s;
       const int l = sl / p.P;
       const int Hl = (int)__ldg(p.shapes + 2 * l), Wl = (int)__ldg(p.shapes + 2 * l + 1);
+      float2 xy;
+      if (EPI) {
+        epi_decode(p, item0, s, (float)Wl, (float)Hl, loc0, att0, xy, aw);
+      } else {
+        xy = __ldg(reinterpret_cast<const float2*>(loc0) + s);
+        aw = __ldg(att0 + s);
+      }
       decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw, p.pix_stride);
       fH = (float)Hl;
       fW = (float)Wl;
@@ -357,8 +402,16 @@ msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
       const float ga = ok ? (hh * hw) * r1 + (hh * lw) * r2 + (lh * hw) * r3 + (lh * lw) * r4 : 0.f;
       const float gx = ok ? fW * aw * (hh * (r2 - r1) + lh * (r4 - r3)) : 0.f;
       const float gy = ok ? fH * aw * (hw * (r3 - r1) + lw * (r4 - r2)) : 0.f;
-      gatt0[s] = ga;
-      reinterpret_cast<float2*>(gloc0)[s] = make_float2(gx, gy);
+      if (EPI) {
+        // through loc = off / (W,H) + ref and w = softmax(logits): grad_off = grad_loc / (W,H),
+        // grad_logit = w * (grad_w - sum_j w_j grad_w_j)   (all 32 lanes take part in the sum)
+        const float dot = warp_sum(aw * ga);
+        gatt0[s] = aw * (ga - dot);
+        reinterpret_cast<float2*>(gloc0)[s] = make_float2(__fdiv_rn(gx, fW), __fdiv_rn(gy, fH));
+      } else {
+        gatt0[s] = ga;
+        reinterpret_cast<float2*>(gloc0)[s] = make_float2(gx, gy);
+      }
     }
   }
 }
@@ -624,6 +677,8 @@ int fill_params(MsdaParams& p, const float* value, const int64_t* shapes, const 
   p.ipw = 1;
   p.lp_shift = 0;
   p.pix_stride = H * C;
+  p.ref = nullptr;
+  p.D = 1;
   return VIDAR_OK;
 }
 
@@ -737,4 +792,60 @@ extern "C" int vidar_msda_backward(const float* value, const int64_t* spatial_sh
     msda_backward_generic_kernel<<<(unsigned)nb, 256, 0, st>>>(p, grad_out, grad_value, grad_sampling_loc, grad_attn_weight);
   }
   return check_launch("ms_deform_attn_backward");
+}
+
+// ---- MSDeformableAttention3D with the softmax and the sampling-location arithmetic folded in
+static int check_sca(MsdaParams& p, const float* ref, int D, const char* who) {
+  VIDAR_REQUIRE(ref, "%s: null reference points", who);
+  VIDAR_REQUIRE(D > 0 && p.P % D == 0, "%s: num_points (%d) must be a multiple of the number of Z anchors (%d)", who, p.P, D);
+  VIDAR_REQUIRE(p.LP == 32, "%s: the fused epilogue needs num_levels * num_points == 32 (got %d)", who, p.LP);
+  VIDAR_REQUIRE(vec_ok(p) && (p.C == 16 || p.C == 32 || p.C == 64), "%s: head dim must be 16, 32 or 64 (got %d)", who, p.C);
+  p.ref = ref;
+  p.D = D;
+  return VIDAR_OK;
+}
+
+extern "C" int vidar_msda_sca_forward(const float* value, const int64_t* spatial_shapes,
+                                      const int64_t* level_start, const float* ref_points,
+                                      const float* offsets, const float* logits, float* out, int B,
+                                      int K, int H, int C, int L, int Q, int P, int D, void* stream) {
+  const char* who = "msda_sca_forward";
+  MsdaParams p;
+  int rc = fill_params(p, value, spatial_shapes, level_start, offsets, logits, B, K, H, C, L, Q, P, B, who);
+  if (rc) return rc;
+  rc = check_sca(p, ref_points, D, who);
+  if (rc) return rc;
+  VIDAR_REQUIRE(out, "%s: null output", who);
+  set_ipw(p, C / 4);
+  const long long nb = num_blocks(p);
+  VIDAR_REQUIRE(nb < 2147483647LL, "%s: problem too large", who);
+  const dim3 grid((unsigned)nb), block(kWarpsPerBlock * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 32) msda_forward_kernel<8, false, true><<<grid, block, 0, st>>>(p, out);
+  else if (C == 16) msda_forward_kernel<4, false, true><<<grid, block, 0, st>>>(p, out);
+  else msda_forward_kernel<16, false, true><<<grid, block, 0, st>>>(p, out);
+  return check_launch(who);
+}
+
+extern "C" int vidar_msda_sca_backward(const float* value, const int64_t* spatial_shapes,
+                                       const int64_t* level_start, const float* ref_points,
+                                       const float* offsets, const float* logits, const float* grad_out,
+                                       float* grad_value, float* grad_offsets, float* grad_logits, int B,
+                                       int K, int H, int C, int L, int Q, int P, int D, void* stream) {
+  const char* who = "msda_sca_backward";
+  MsdaParams p;
+  int rc = fill_params(p, value, spatial_shapes, level_start, offsets, logits, B, K, H, C, L, Q, P, B, who);
+  if (rc) return rc;
+  rc = check_sca(p, ref_points, D, who);
+  if (rc) return rc;
+  VIDAR_REQUIRE(grad_out && grad_value && grad_offsets && grad_logits, "%s: null gradient pointer", who);
+  set_ipw(p, C / 4);
+  const long long nb = num_blocks(p);
+  VIDAR_REQUIRE(nb < 2147483647LL, "%s: problem too large", who);
+  const dim3 grid((unsigned)nb), block(kWarpsPerBlock * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 32) msda_backward_kernel<8, false, true><<<grid, block, 0, st>>>(p, grad_out, grad_value, grad_offsets, grad_logits);
+  else if (C == 16) msda_backward_kernel<4, false, true><<<grid, block, 0, st>>>(p, grad_out, grad_value, grad_offsets, grad_logits);
+  else msda_backward_kernel<16, false, true><<<grid, block, 0, st>>>(p, grad_out, grad_value, grad_offsets, grad_logits);
+  return check_launch(who);
 }

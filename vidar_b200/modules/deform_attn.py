@@ -22,10 +22,11 @@ import warnings
 import torch
 import torch.nn as nn
 
-from ..msda import MultiScaleDeformableAttnFunction_fp32
+from ..msda import MSDeformAttn3DFusedFunction, MultiScaleDeformableAttnFunction_fp32
 from ..registry import ATTENTION, BaseModule, build_attention, constant_init, xavier_init
 
 msda_apply = MultiScaleDeformableAttnFunction_fp32.apply
+msda3d_fused_apply = MSDeformAttn3DFusedFunction.apply
 
 
 def _check_heads(embed_dims, num_heads):
@@ -76,6 +77,7 @@ class MSDeformableAttention3D(BaseModule):
         self.sampling_offsets = nn.Linear(embed_dims, num_heads * num_levels * num_points * 2)
         self.attention_weights = nn.Linear(embed_dims, num_heads * num_levels * num_points)
         self.value_proj = nn.Linear(embed_dims, embed_dims)
+        self.fuse_epilogue = True      # False: materialise sampling_locations / attention_weights like the reference
         self.init_weights()
 
     def init_weights(self):
@@ -104,14 +106,19 @@ class MSDeformableAttention3D(BaseModule):
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, H, -1)
         offsets = self.sampling_offsets(query).view(bs, num_query, H, L, P, 2)
-        weights = self.attention_weights(query).view(bs, num_query, H, L * P).softmax(-1)
-        weights = weights.view(bs, num_query, H, L, P)
+        logits = self.attention_weights(query).view(bs, num_query, H, L * P)
 
         if reference_points.shape[-1] != 2:
             raise ValueError(f"Last dim of reference_points must be 2, but get {reference_points.shape[-1]} instead.")
         # point p = j * D + z samples around Z-anchor z  (:356-371)
         D = reference_points.shape[2]
         assert P % D == 0
+        if (self.fuse_epilogue and value.is_cuda and value.dtype == torch.float32 and not torch.is_autocast_enabled()
+                and MSDeformAttn3DFusedFunction.supported(L, P, value.shape[-1], D)):
+            # softmax and the sampling-location arithmetic run inside the kernel (no loc / weights tensors)
+            output = msda3d_fused_apply(value, spatial_shapes, level_start_index, reference_points, offsets, logits)
+            return output if self.batch_first else output.permute(1, 0, 2)
+        weights = logits.softmax(-1).view(bs, num_query, H, L, P)
         offsets = offsets / _wh(spatial_shapes)[None, None, None, :, None, :]
         loc = offsets.view(bs, num_query, H, L, P // D, D, 2) + reference_points[:, :, None, None, None, :, :]
         loc = loc.view(bs, num_query, H, L, P, 2)

@@ -158,3 +158,59 @@ class MultiScaleDeformableAttnFunction_fp16(MultiScaleDeformableAttnFunction_fp3
             ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
             attention_weights, im2col_step)
         return out.half()
+
+
+class MSDeformAttn3DFusedFunction(Function):
+    """MSDeformableAttention3D's sampling with its elementwise prologue inside the kernel
+    (spatial_cross_attention.py:339-371): softmax over the L*P logits of a (query, head) and
+    loc = offsets / (W_l, H_l) + reference_points_cam[..., p % D, :].  Never materialises
+    `sampling_locations` / `attention_weights` (0.74 GB at 6 x 40000 queries) nor their gradients.
+
+    apply(value [B,K,H,C], spatial_shapes, level_start_index, reference_points [B,Q,D,2],
+          offsets [B,Q,H,L,P,2] (raw Linear output), logits [B,Q,H,L*P]) -> [B,Q,H*C]
+    Gradients: value, offsets, logits (reference points come from the camera geometry)."""
+
+    @staticmethod
+    def supported(num_levels, num_points, head_dim, num_anchors):
+        return num_levels * num_points == 32 and head_dim in (16, 32, 64) and num_points % num_anchors == 0
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, offsets, logits):
+        _lib.require_cuda(value=value.contiguous(), offsets=offsets.contiguous())
+        value = value.float().contiguous()
+        ref = reference_points.float().contiguous()
+        offsets = offsets.float().contiguous()
+        logits = logits.float().contiguous()
+        spatial_shapes = spatial_shapes.contiguous()
+        level_start_index = level_start_index.contiguous()
+        B, K, H, C = value.shape
+        Q, D = ref.shape[1], ref.shape[2]
+        L = spatial_shapes.shape[0]
+        P = offsets.numel() // (B * Q * H * L * 2)
+        if tuple(ref.shape) != (B, Q, D, 2) or logits.numel() != B * Q * H * L * P:
+            raise RuntimeError("reference_points must be [B,Q,D,2], offsets [B,Q,H,L,P,2], logits [B,Q,H,L*P]")
+        out = torch.empty((B, Q, H * C), dtype=torch.float32, device=value.device)
+        with torch.cuda.device(value.device):
+            _lib.check(_lib.lib().vidar_msda_sca_forward(
+                _lib.ptr(value), _lib.ptr(spatial_shapes), _lib.ptr(level_start_index), _lib.ptr(ref), _lib.ptr(offsets),
+                _lib.ptr(logits), _lib.ptr(out), B, K, H, C, L, Q, P, D, _lib.stream_ptr(value.device)))
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, ref, offsets, logits)
+        ctx.dims = (B, K, H, C, L, Q, P, D)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, spatial_shapes, level_start_index, ref, offsets, logits = ctx.saved_tensors
+        B, K, H, C, L, Q, P, D = ctx.dims
+        grad_output = grad_output.float().contiguous()
+        grad_value = torch.zeros_like(value)
+        grad_offsets = torch.empty_like(offsets)
+        grad_logits = torch.empty_like(logits)
+        with torch.cuda.device(value.device):
+            _lib.check(_lib.lib().vidar_msda_sca_backward(
+                _lib.ptr(value), _lib.ptr(spatial_shapes), _lib.ptr(level_start_index), _lib.ptr(ref), _lib.ptr(offsets),
+                _lib.ptr(logits), _lib.ptr(grad_output), _lib.ptr(grad_value), _lib.ptr(grad_offsets),
+                _lib.ptr(grad_logits), B, K, H, C, L, Q, P, D, _lib.stream_ptr(value.device)))
+        return grad_value, None, None, None, grad_offsets, grad_logits
+
