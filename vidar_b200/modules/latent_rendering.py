@@ -16,6 +16,7 @@ cells over a process group.  Other configurations keep the Linear layers as PyTo
 around the custom core.  CUDA only.
 """
 import torch
+from torch.autograd.function import once_differentiable
 import torch.nn as nn
 
 from .. import _lib
@@ -48,6 +49,7 @@ class _LatentRenderCore(torch.autograd.Function):
         return prob, pooled
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_prob, grad_pooled):
         occ, feat, prob, pooled, aux = ctx.saved_tensors
         grid_num, grid_step, eps, act = ctx.cfg
@@ -107,6 +109,7 @@ class _ShardedLatentRenderCore(torch.autograd.Function):
         return prob, pooled
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_prob, grad_pooled):
         import torch.distributed as dist
         occ, feat, prob, pooled, aux = ctx.saved_tensors
@@ -199,6 +202,7 @@ class _FusedLatentRendering(torch.autograd.Function):
         return out.view(bs, Hb, Wb, E)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         import torch.distributed as dist
         from ..sharding import gather_rows

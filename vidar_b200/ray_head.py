@@ -16,6 +16,7 @@ Low-level autograd ops: `ray_sample` (logits/lengths, differentiable w.r.t. sigm
 All tensors must be CUDA; there is no PyTorch fallback.
 """
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -58,6 +59,7 @@ class _RaySample(torch.autograd.Function):
         return logits, length, valid
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_logits, _gl, _gv):
         origin, points, frame = ctx.saved_tensors
         shape, num_way, step, with_gt = ctx.meta
@@ -95,6 +97,7 @@ class _RayCE(torch.autograd.Function):
         return ce, valid
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_ce, _gv):
         sigma, origin, points, frame, lse = ctx.saved_tensors
         num_way, step = ctx.meta

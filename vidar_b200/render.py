@@ -22,6 +22,7 @@ cudaDeviceSynchronize after every launch, dvr.cu:379,688,735; callers do not rel
 import types
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -193,6 +194,7 @@ class DifferentiableVoxelRenderingLayer(torch.autograd.Function):
         return pred_dist, gt_dist
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gradpred, gradgt):
         sigma, origin, points, tindex = ctx.saved_tensors
         grad_sigma, _ = _backward_fused(sigma, origin, points, tindex, gradpred)
@@ -210,6 +212,7 @@ class DifferentiableVoxelRenderingLayerLists(torch.autograd.Function):
         return pred_dist, gt_dist
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gradpred, gradgt):
         dd_dsigma, indices, tindex, sigma_shape = ctx.saved_tensors
         elementwise_mult = gradpred[..., None] * dd_dsigma
@@ -232,6 +235,7 @@ class DifferentiableVoxelRenderingLayerV2(torch.autograd.Function):
         return pred_dist, gt_dist, ray_pred, indicator
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gradpred, gradgt, grad_ray_pred, grad_indicator):
         sigma, origin, points, tindex = ctx.saved_tensors
         grad_sigma, grad_sigma_regul = _backward_fused(sigma, origin, points, tindex, gradpred,
