@@ -72,3 +72,51 @@ def get_bev_grids(H, W, bs=1, device="cuda", dtype=torch.float, offset=0.5):
 
 def get_bev_grids_3d(H, W, Z, bs=1, device="cuda", dtype=torch.float):
     return get_reference_points(H, W, Z, Z, "3d", bs, device, dtype)
+
+
+def flatten_fpn(mlvl_feats, cams_embeds=None, level_embeds=None):
+    """PerceptionTransformer.get_bev_features' feature flattening (modules/transformer.py:159-179):
+    list of [bs, cams, C, h, w] -> (feat_flatten [cams, sum(hw), bs, C], spatial_shapes [L,2] int64,
+    level_start_index [L] int64), camera / level embeddings added when given."""
+    flat, shapes = [], []
+    for lvl, feat in enumerate(mlvl_feats):
+        bs, cams, c, h, w = feat.shape
+        f = feat.flatten(3).permute(1, 0, 3, 2)
+        if cams_embeds is not None:
+            f = f + cams_embeds[:, None, None, :].to(f.dtype)
+        if level_embeds is not None:
+            f = f + level_embeds[None, None, lvl:lvl + 1, :].to(f.dtype)
+        shapes.append((h, w))
+        flat.append(f)
+    flat = torch.cat(flat, 2).permute(0, 2, 1, 3)
+    shapes = torch.as_tensor(shapes, dtype=torch.long, device=flat.device)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    return flat, shapes, lsi
+
+
+def value_from_fpn(mlvl_feats, cams_embeds, level_embeds, value_proj, num_heads):
+    """Producer side of the MSDA value layout: the `value` tensor
+    MSDeformableAttention3D samples, `value_proj(feat_flatten)` viewed [bs*cams, sum(hw), H, C]
+    (spatial_cross_attention.py:158-160,333-336), straight from the FPN maps.  The camera and level
+    embeddings are folded into a per-(camera, level) bias,
+        value = feat^T W^T + (W (cam_e + lvl_e) + b),
+    and each level is one batched GEMM that reads the NCHW map transposed, so `feat_flatten`
+    (190 MB at 6 x 30825 x 256) and its three elementwise passes are never materialised.
+    Returns (value [bs*cams, sum(hw), num_heads, C/num_heads], spatial_shapes, level_start_index);
+    rows are ordered (bs, cams) like SpatialCrossAttention's `value.permute(2,0,1,3).reshape(bs*cams, ...)`."""
+    W, b = value_proj.weight, value_proj.bias
+    outs, shapes = [], []
+    for lvl, feat in enumerate(mlvl_feats):
+        bs, cams, c, h, w = feat.shape
+        e = level_embeds[lvl].to(feat.dtype).expand(cams, -1)
+        if cams_embeds is not None:
+            e = e + cams_embeds.to(feat.dtype)
+        bias = torch.nn.functional.linear(e, W, b)                                 # [cams, C_out]
+        a = feat.reshape(bs * cams, c, h * w).transpose(1, 2)                      # [bs*cams, hw, c] view of NCHW
+        v = torch.baddbmm(bias.repeat(bs, 1)[:, None, :], a, W.t().expand(bs * cams, -1, -1))
+        outs.append(v)
+        shapes.append((h, w))
+    value = torch.cat(outs, 1)
+    shapes = torch.as_tensor(shapes, dtype=torch.long, device=value.device)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    return value.view(value.shape[0], value.shape[1], num_heads, -1), shapes, lsi
