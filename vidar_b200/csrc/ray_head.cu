@@ -74,10 +74,10 @@ __device__ __forceinline__ Sample make_sample(const RayDims& D, const RaySetup& 
   const float nz = __fsub_rn(__fmul_rn(__fdiv_rn(z, (float)D.Z), 2.f), 1.f);
   // `(grid <= -1) | (grid >= 1)`: NaN compares false -> not masked, like the reference
   q.masked = (nx <= -1.f) || (nx >= 1.f) || (ny <= -1.f) || (ny >= 1.f) || (nz <= -1.f) || (nz >= 1.f);
-  // grid_sample un-normalisation, align_corners=False: ((n + 1) * size - 1) / 2
-  q.ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(nx, 1.f), (float)D.X), 1.f), 2.f);
-  q.iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(ny, 1.f), (float)D.Y), 1.f), 2.f);
-  q.iz = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(nz, 1.f), (float)D.Z), 1.f), 2.f);
+  // grid_sample un-normalisation, align_corners=False: ((n + 1) * size - 1) / 2 (x 0.5: same bits)
+  q.ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(nx, 1.f), (float)D.X), 1.f), 0.5f);
+  q.iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(ny, 1.f), (float)D.Y), 1.f), 0.5f);
+  q.iz = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(nz, 1.f), (float)D.Z), 1.f), 0.5f);
   return q;
 }
 
