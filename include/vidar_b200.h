@@ -225,6 +225,22 @@ int vidar_ray_argmax(const float* sigma, const float* origin, const float* point
                      const int32_t* frame, float* depth, float* index,
                      int R, int F, int Z, int Y, int X, int num_way, float step, void* stream);
 
+/* Fused gumbel decode of the dense loss term: ViDARHeadBase._custom_gumbel_softmax_distance
+ * (vidar_head_base.py:754-773) applied to the sampler's logits without the GT slot (:631-636).
+ *   noise [R, num_way]  Gumbel(0,1) noise, drawn by the host like F.gumbel_softmax draws it
+ *   dist  [R]           length of the sampled waypoint (0 for rays whose end point is outside)
+ *   lse, p_next [R]     saved for the backward (log-sum-exp of the logits, softmax mass beyond dist)
+ * Backward: grad_sigma (caller-zeroed) += grad_dist[r] * dist[r] * softmax_k * ([len_k > dist[r]] - p_next[r]). */
+int vidar_ray_gumbel_forward(const float* sigma, const float* origin, const float* points,
+                             const int32_t* frame, const float* noise, float* dist, float* lse,
+                             float* p_next, int R, int F, int Z, int Y, int X, int num_way,
+                             float step, void* stream);
+int vidar_ray_gumbel_backward(const float* sigma, const float* origin, const float* points,
+                              const int32_t* frame, const float* dist, const float* lse,
+                              const float* p_next, const float* grad_dist, float* grad_sigma,
+                              int R, int F, int Z, int Y, int X, int num_way, float step,
+                              void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (ii-c) LatentRendering core
  *   (projects/mmdet3d_plugin/bevformer/modules/ray_operations/latent_rendering.py:98-161:

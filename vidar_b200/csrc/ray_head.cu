@@ -238,6 +238,88 @@ ray_ce_bwd_kernel(RayDims D, const float* __restrict__ sigma, const float* __res
   }
 }
 
+// ---- fused gumbel decode of the dense loss term --------------------------------------------
+// ViDARHeadBase._custom_gumbel_softmax_distance (vidar_head_base.py:754-773) on the sampler's
+// logits without the GT slot (`dense_feat_total[0][..., 1:]`, :631-636), per ray:
+//   idx   = argmax_k (logit_k + gumbel_k)                 F.gumbel_softmax(hard=True), forward value
+//   pred  = length_idx                                    ((1 - s) + s == 1 exactly in fp32)
+//   p     = sum_{length_k > pred} e^{logit_k} / sum_k e^{logit_k}
+//   out   = (1 - p.detach() + p) * pred  = pred,          d out / d logit_j = pred * softmax_j * ([length_j > pred] - p)
+// The [rays, 512] logits, softmax and one-hot tensors of the reference are never written; the
+// noise is an input (drawn by the host exactly like F.gumbel_softmax draws it).
+__global__ void __launch_bounds__(kRaysPerBlock * 32)
+ray_gumbel_fwd_kernel(RayDims D, const float* __restrict__ sigma, const float* __restrict__ origin,
+                      const float* __restrict__ points, const int32_t* __restrict__ frame,
+                      const float* __restrict__ noise, float* __restrict__ dist,
+                      float* __restrict__ lse_out, float* __restrict__ p_out) {
+  const int r = blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= D.R) return;
+  const RaySetup s = load_ray(D, origin, points, frame, r);
+  if (!gt_inside(D, s)) {
+    if (lane == 0) { dist[r] = 0.f; lse_out[r] = 0.f; p_out[r] = 0.f; }
+    return;
+  }
+  const float* vol = sigma + (size_t)s.f * D.Z * D.Y * D.X;
+  const float* nz = noise + (size_t)r * D.num_way;
+  float m = -INFINITY, acc = 0.f, best = -INFINITY, best_len = 0.f;
+  int best_k = 0x7fffffff;
+  for (int k = 1 + lane; k <= D.num_way; k += 32) {
+    const Sample q = make_sample(D, s, k);
+    const float v = q.masked ? -INFINITY : trilinear(vol, corners(D, q));
+    const float y = v + __ldg(nz + k - 1);
+    if (best_k == 0x7fffffff || y > best) { best = y; best_k = k; best_len = q.length; }
+    if (v > m) { acc = acc * expf(m - v) + 1.f; m = v; }
+    else if (v > -INFINITY) acc += expf(v - m);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {   // warp arg-max, smallest index wins ties
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+    const float ol = __shfl_xor_sync(0xffffffffu, best_len, o);
+    if (ov > best || (ov == best && ok < best_k)) { best = ov; best_k = ok; best_len = ol; }
+  }
+  const float M = warp_max(m);
+  const float S = warp_sum((m == -INFINITY) ? 0.f : acc * expf(m - M));
+  float nx = 0.f;
+  for (int k = 1 + lane; k <= D.num_way; k += 32) {
+    const Sample q = make_sample(D, s, k);
+    if (q.masked || !(q.length > best_len)) continue;
+    nx += expf(trilinear(vol, corners(D, q)) - M);
+  }
+  nx = warp_sum(nx);
+  if (lane == 0) { dist[r] = best_len; lse_out[r] = M + logf(S); p_out[r] = nx / S; }
+}
+
+__global__ void __launch_bounds__(kRaysPerBlock * 32)
+ray_gumbel_bwd_kernel(RayDims D, const float* __restrict__ sigma, const float* __restrict__ origin,
+                      const float* __restrict__ points, const int32_t* __restrict__ frame,
+                      const float* __restrict__ dist, const float* __restrict__ lse_in,
+                      const float* __restrict__ p_in, const float* __restrict__ grad_dist,
+                      float* __restrict__ grad_sigma) {
+  const int r = blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= D.R) return;
+  const float pred = dist[r];
+  const float g = grad_dist[r] * pred;
+  if (g == 0.f) return;
+  const RaySetup s = load_ray(D, origin, points, frame, r);
+  if (!gt_inside(D, s)) return;
+  const size_t voff = (size_t)s.f * D.Z * D.Y * D.X;
+  const float* vol = sigma + voff;
+  float* gvol = grad_sigma + voff;
+  const float lse = lse_in[r], p = p_in[r];
+  for (int k = 1 + lane; k <= D.num_way; k += 32) {
+    const Sample q = make_sample(D, s, k);
+    if (q.masked) continue;
+    const Corners c = corners(D, q);
+    const float dl = g * expf(trilinear(vol, c) - lse) * ((q.length > pred ? 1.f : 0.f) - p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c.idx[j] >= 0) red_add_f32(gvol + c.idx[j], dl * c.w[j]);
+  }
+}
+
 // ---- inference decode: zeros -> -inf, first arg-max, its length ---------------------------
 __global__ void __launch_bounds__(kRaysPerBlock * 32)
 ray_argmax_kernel(RayDims D, const float* __restrict__ sigma, const float* __restrict__ origin,
@@ -353,4 +435,34 @@ extern "C" int vidar_ray_argmax(const float* sigma, const float* origin, const f
   ray_argmax_kernel<<<ray_blocks(R), kRaysPerBlock * 32, 0, (cudaStream_t)stream>>>(
       D, sigma, origin, points, frame, depth, index);
   return check_launch("ray_argmax");
+}
+
+extern "C" int vidar_ray_gumbel_forward(const float* sigma, const float* origin, const float* points,
+                                        const int32_t* frame, const float* noise, float* dist, float* lse,
+                                        float* p_next, int R, int F, int Z, int Y, int X, int num_way,
+                                        float step, void* stream) {
+  RayDims D;
+  int rc = check_dims(D, R, F, Z, Y, X, num_way, step, 1, "ray_gumbel_forward");
+  if (rc) return rc;
+  if (R == 0) return VIDAR_OK;
+  VIDAR_REQUIRE(sigma && origin && points && noise && dist && lse && p_next, "ray_gumbel_forward: null pointer argument");
+  ray_gumbel_fwd_kernel<<<ray_blocks(R), kRaysPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      D, sigma, origin, points, frame, noise, dist, lse, p_next);
+  return check_launch("ray_gumbel_forward");
+}
+
+extern "C" int vidar_ray_gumbel_backward(const float* sigma, const float* origin, const float* points,
+                                         const int32_t* frame, const float* dist, const float* lse,
+                                         const float* p_next, const float* grad_dist, float* grad_sigma,
+                                         int R, int F, int Z, int Y, int X, int num_way, float step,
+                                         void* stream) {
+  RayDims D;
+  int rc = check_dims(D, R, F, Z, Y, X, num_way, step, 1, "ray_gumbel_backward");
+  if (rc) return rc;
+  if (R == 0) return VIDAR_OK;
+  VIDAR_REQUIRE(sigma && origin && points && dist && lse && p_next && grad_dist && grad_sigma,
+                "ray_gumbel_backward: null pointer argument");
+  ray_gumbel_bwd_kernel<<<ray_blocks(R), kRaysPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      D, sigma, origin, points, frame, dist, lse, p_next, grad_dist, grad_sigma);
+  return check_launch("ray_gumbel_backward");
 }

@@ -13,9 +13,9 @@ arguments, returned keys and arithmetic
   _custom_gumbel_softmax_distance  :754-773
 
 What runs where: the CE term never materialises the [levels, rays, 513] logits
-(`ray_head.ce_regularization_loss`, one fused kernel per frame set); the dense term and the
-distance term sample through `ray_head.get_grid_features` (CUDA sampler) and then follow the
-reference's torch statements; Chamfer uses the nearest-neighbour kernel (`chamfer.knn_points`) in
+(`ray_head.ce_regularization_loss`, one fused kernel per frame set); the dense term's gumbel decode
+is fused with the sampler as well (`ray_head.gumbel_distance`); the distance term samples through
+`ray_head.get_grid_features` (CUDA sampler) and then follows the reference's torch statements; Chamfer uses the nearest-neighbour kernel (`chamfer.knn_points`) in
 place of mmdet3d's O(N*M) distance matrix (`chamfer_distance`, criterion 'l2', reduction 'mean':
 the mean squared NN distance each way); decoding is `ray_head.decode_ray_depth`.
 CUDA only, like everything else in this package.
@@ -58,6 +58,7 @@ class ViDARRayHead:
         self.loss_weight = np.array(loss_weight)
         assert self.loss_weight.shape[-1] == 1
         self.eval_within_grid = eval_within_grid
+        self.fuse_dense_decode = True     # False: dense term through the materialising sampler + torch statements
 
     # ------------------------------------------------------------------ ground truth (:219-276)
     def _process_gt_points(self, bev_preds, gt_points, batched_origin_points, valid_frames, start_idx,
@@ -162,12 +163,26 @@ class ViDARRayHead:
             ones = voxel_grids.new_ones(*voxel_grids.shape[:2]).to(gt_tindex.dtype)
             voxel_grids = torch.cat([voxel_grids for _ in range(valid_frame_num)], 1)
             voxel_tindex = torch.cat([ones * i for i in range(valid_frame_num)], 1)
-            _, d_feat, _, d_len = ray_head.get_grid_features(
-                origin_grids, voxel_grids, voxel_tindex, [tgt], np.array([[1]] * valid_frame_num), step,
-                self.ray_grid_num, return_as_batch=True)
-            d_feat = d_feat[0][..., 1:].contiguous()
-            d_len = d_len[..., 1:].contiguous()
-            dense_dist = self._custom_gumbel_softmax_distance(d_feat, d_len, gumbels.get("dense"))
+            if self.fuse_dense_decode:
+                # sampler + gumbel decode in one kernel per batch element: the [bs, rays, ray_grid_num]
+                # logits / softmax / one-hot tensors are never written.  The noise is drawn with the
+                # statement F.gumbel_softmax uses, on the shape its logits would have.
+                noise = gumbels.get("dense")
+                if noise is None:
+                    noise = -torch.empty((bs, voxel_grids.shape[1], self.ray_grid_num), dtype=torch.float32,
+                                         device=sigma.device).exponential_().log()
+                frame = voxel_tindex[0].to(torch.int32).contiguous()
+                dense_dist = torch.stack([
+                    ray_head.gumbel_distance(tgt[b], origin_grids[b, :valid_frame_num].contiguous().float(),
+                                             voxel_grids[b].contiguous(), frame, self.ray_grid_num, step, noise[b])
+                    for b in range(bs)])
+            else:
+                _, d_feat, _, d_len = ray_head.get_grid_features(
+                    origin_grids, voxel_grids, voxel_tindex, [tgt], np.array([[1]] * valid_frame_num), step,
+                    self.ray_grid_num, return_as_batch=True)
+                d_feat = d_feat[0][..., 1:].contiguous()
+                d_len = d_len[..., 1:].contiguous()
+                dense_dist = self._custom_gumbel_softmax_distance(d_feat, d_len, gumbels.get("dense"))
             voxel_pcd = self.get_rendered_pcds(origin_grids, voxel_grids, voxel_tindex, dense_dist, dense_dist, tgt_pc_range)
             dense = 0
             for b in range(bs):

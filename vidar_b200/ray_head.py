@@ -117,6 +117,46 @@ def ray_ce(sigma, origin, points, frame, num_way, step):
     return _RayCE.apply(sigma, origin.contiguous(), points.contiguous(), frame, num_way, step)
 
 
+class _RayGumbel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sigma, origin, points, frame, noise, num_way, step):
+        sigma = sigma.contiguous()
+        R, F, Z, Y, X = _prep(sigma, origin, points, frame)
+        noise = noise.float().contiguous()
+        if tuple(noise.shape) != (R, int(num_way)):
+            raise RuntimeError(f"noise must be [rays, num_way] = {(R, int(num_way))}, got {tuple(noise.shape)}")
+        out = torch.zeros((3, R), dtype=torch.float32, device=sigma.device)      # dist, lse, p_next
+        if R:
+            _call(_lib.lib().vidar_ray_gumbel_forward, sigma.device, _lib.ptr(sigma), _lib.ptr(origin),
+                  _lib.ptr(points), _lib.ptr(frame), _lib.ptr(noise), _lib.ptr(out[0]), _lib.ptr(out[1]),
+                  _lib.ptr(out[2]), R, F, Z, Y, X, int(num_way), float(step))
+        ctx.save_for_backward(sigma, origin, points, frame, out)
+        ctx.meta = (int(num_way), float(step))
+        return out[0].clone()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_dist):
+        sigma, origin, points, frame, out = ctx.saved_tensors
+        num_way, step = ctx.meta
+        F, Z, Y, X = sigma.shape
+        grad_sigma = torch.zeros_like(sigma)
+        R = points.shape[0]
+        if R:
+            g = grad_dist.float().contiguous()
+            _call(_lib.lib().vidar_ray_gumbel_backward, sigma.device, _lib.ptr(sigma), _lib.ptr(origin),
+                  _lib.ptr(points), _lib.ptr(frame), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
+                  _lib.ptr(g), _lib.ptr(grad_sigma), R, F, Z, Y, X, num_way, step)
+        return grad_sigma, None, None, None, None, None, None
+
+
+def gumbel_distance(sigma, origin, points, frame, num_way, step, noise):
+    """Fused sampler + `_custom_gumbel_softmax_distance` (vidar_head_base.py:754-773) over the
+    num_way waypoints of every ray (no GT slot): sigma [F,Z,Y,X], origin [F,3], points [R,3],
+    frame int32 [R], noise [R,num_way] Gumbel(0,1) -> dist [R], differentiable in sigma."""
+    return _RayGumbel.apply(sigma, origin.contiguous(), points.contiguous(), frame, noise, num_way, step)
+
+
 def ray_argmax(sigma, origin, points, frame, num_way, step):
     """-> (depth [R] voxel units, index [R] float) of the arg-max waypoint."""
     sigma = sigma.contiguous()
