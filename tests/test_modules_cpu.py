@@ -74,3 +74,27 @@ def test_modules_have_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
         m(c["query"], None, c["value"], reference_points=c["reference_points"],
           spatial_shapes=c["spatial_shapes"], level_start_index=c["level_start_index"])
+
+
+def test_visible_lists_are_cached_per_mask_tensor(monkeypatch):
+    """SCA's rebatching lists are computed once per `bev_mask` tensor (the encoder passes the same
+    tensor to every layer): same object + same version -> cached; in-place edit or new tensor -> recomputed."""
+    calls = []
+    real = torch.argsort
+    monkeypatch.setattr(torch, "argsort", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    deform_attn._VISIBLE_CACHE.clear()
+    c = mc.sca_case()
+    mask = c["bev_mask"]
+    a = deform_attn._visible_lists(mask)
+    b = deform_attn._visible_lists(mask)
+    assert len(calls) == 1 and a[0] is b[0]
+    idx, live, max_len = a
+    hit = mask[:, 0].sum(-1) > 0
+    for cam in range(mask.shape[0]):
+        want = hit[cam].nonzero().squeeze(-1)                      # the reference's index_query_per_img
+        assert torch.equal(idx[cam][live[cam]], want)
+    assert max_len == int(hit.sum(-1).max())
+    mask[0, 0, 0, 0] = ~mask[0, 0, 0, 0]                           # in-place change bumps the version
+    deform_attn._visible_lists(mask)
+    deform_attn._visible_lists(mask.clone())
+    assert len(calls) == 3

@@ -129,6 +129,30 @@ class MSDeformableAttention3D(BaseModule):
         return output
 
 
+_VISIBLE_CACHE = []      # [(weakref(bev_mask), version, (idx, live, max_len))], newest first
+
+
+def _visible_lists(bev_mask):
+    """Per-camera lists of visible pillars (batch element 0, spatial_cross_attention.py:136-140) as
+    (idx [cams, max_len] ascending pillar indices padded with invisible ones, live [cams, max_len]
+    bool, max_len).  One batched stable sort instead of six `nonzero()` calls and ONE host sync
+    (max_len); the encoder hands the same `bev_mask` tensor to all of its layers, so the lists are
+    cached on the tensor object (identity + in-place version): one sync per encoder call."""
+    import weakref
+    for ref, version, lists in _VISIBLE_CACHE:
+        if ref() is bev_mask and version == bev_mask._version:
+            return lists
+    hit = bev_mask[:, 0].sum(-1) > 0                                     # [cams, Q]
+    counts = hit.sum(-1)
+    max_len = int(counts.max())
+    order = torch.argsort((~hit).to(torch.uint8), dim=1, stable=True)    # visible first, ascending
+    idx = order[:, :max_len].contiguous()
+    live = torch.arange(max_len, device=bev_mask.device)[None, :] < counts[:, None]
+    _VISIBLE_CACHE.insert(0, (weakref.ref(bev_mask), bev_mask._version, (idx, live, max_len)))
+    del _VISIBLE_CACHE[2:]
+    return idx, live, max_len
+
+
 @ATTENTION.register_module()
 class SpatialCrossAttention(BaseModule):
     """BEV query -> 6 camera feature pyramids (spatial_cross_attention.py:30-174): each camera
@@ -167,14 +191,8 @@ class SpatialCrossAttention(BaseModule):
         bs, num_query, C = query.shape
         cams, D = self.num_cams, reference_points_cam.size(3)
 
-        # visible-pillar lists per camera, taken from batch element 0 like the reference (:136-140).
-        # One batched sort instead of 6 nonzero() calls; ONE host sync (max_len).
-        hit = bev_mask[:, 0].sum(-1) > 0                                     # [cams, Q]
-        counts = hit.sum(-1)
-        max_len = int(counts.max())
-        order = torch.argsort((~hit).to(torch.uint8), dim=1, stable=True)    # visible first, ascending
-        idx = order[:, :max_len]                                             # [cams, max_len]
-        live = torch.arange(max_len, device=query.device)[None, :] < counts[:, None]
+        # visible-pillar lists per camera, taken from batch element 0 like the reference (:136-140)
+        idx, live, max_len = _visible_lists(bev_mask)
 
         # rebatch (:143-152): padded rows are zeros
         q_re = query[:, idx] * live[None, :, :, None].to(query.dtype)        # [bs, cams, max_len, C]
