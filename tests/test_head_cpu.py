@@ -32,21 +32,41 @@ def test_process_gt_points_matches_reference():
     assert float(op0.abs().sum()) == 0 and torch.allclose(og0[0, 0], torch.tensor([hc.BEV_W / 2, hc.BEV_H / 2, hc.Z / 2]))
 
 
-def test_gumbel_distance_with_given_noise_equals_torch_draw():
+def _reference_gumbel_statements(grid_embed, grid_length):
+    """vidar_head_base.py:754-773, statement by statement (test-side restatement)."""
+    import torch.nn.functional as F
+    pred_dist = F.gumbel_softmax(grid_embed, hard=True)
+    pred_dist = (pred_dist * grid_length).sum(-1).detach()
+    grid_embed = grid_embed - grid_embed.max(-1, keepdims=True)[0]
+    exp_embed = torch.exp(grid_embed)
+    exp_whole = exp_embed.sum(-1)
+    next_ind = (grid_length > pred_dist.unsqueeze(-1)).float()
+    prob_next = (exp_embed * next_ind).sum(-1) / exp_whole
+    prob_next = 1 - prob_next.detach() + prob_next
+    return prob_next * pred_dist
+
+
+def test_gumbel_distance_equals_reference_statements_and_given_noise():
     head, _ = _head()
     g = torch.Generator().manual_seed(3)
-    embed = torch.randn(2, 17, 20, generator=g).requires_grad_(True)
+    embed = torch.randn(2, 17, 20, generator=g)
+    embed[0, 3, 12:] = float("-inf")                      # waypoints outside the volume
     length = (torch.arange(20.0) + 0.5).expand(2, 17, 20)
+    e1, e2, e3 = (embed.clone().requires_grad_(True) for _ in range(3))
     torch.manual_seed(5)
-    a = head._custom_gumbel_softmax_distance(embed, length)
+    ref = _reference_gumbel_statements(e1, length)
+    torch.manual_seed(5)
+    a = head._custom_gumbel_softmax_distance(e2, length)  # draws its own noise: same generator consumption
     torch.manual_seed(5)
     noise = -torch.empty_like(embed).exponential_().log()
-    b = head._custom_gumbel_softmax_distance(embed, length, noise)
-    assert torch.equal(a, b)
-    # value = sampled waypoint length, gradient flows only through the "mass beyond it" term
-    assert set(np.unique(a.detach().numpy())) <= set(np.unique(length.numpy()))
-    (ga,) = torch.autograd.grad(a.sum(), embed)
-    assert torch.isfinite(ga).all() and float(ga.abs().sum()) > 0
+    b = head._custom_gumbel_softmax_distance(e3, length, noise)
+    assert torch.equal(a, ref) and torch.equal(b, ref)
+    assert set(np.unique(ref.detach().numpy())) <= set(np.unique(length.numpy()))
+    w = torch.randn(2, 17, generator=g)
+    for out, e in ((ref, e1), (a, e2), (b, e3)):
+        (out * w).sum().backward()
+    assert torch.allclose(e2.grad, e1.grad, rtol=1e-6, atol=1e-7) and torch.equal(e2.grad, e3.grad)
+    assert float(e1.grad.abs().sum()) > 0 and float(e1.grad[0, 3, 12:].abs().sum()) == 0
 
 
 def test_rendered_pcds_and_inside_mask():

@@ -102,23 +102,20 @@ class ViDARRayHead:
         return pcds
 
     def _custom_gumbel_softmax_distance(self, grid_embed, grid_length, gumbels=None):
-        """:754-773.  `gumbels`: optional pre-drawn Gumbel(0,1) noise of grid_embed's shape (tests pin the
-        reference's CPU draw this way); None draws exactly like F.gumbel_softmax on the tensor's device."""
+        """:754-773: sample one waypoint per ray by Gumbel-max, return its length with the gradient of
+        `length * P(a waypoint beyond it)` (straight-through on the probability).
+        `gumbels`: optional pre-drawn Gumbel(0,1) noise of grid_embed's shape (tests pin the reference's
+        CPU draw this way); None draws with the statement F.gumbel_softmax uses, so the generator is
+        consumed exactly like in the reference.  The hard one-hot of F.gumbel_softmax is
+        `y_hard - y_soft.detach() + y_soft`, whose picked entry is exactly 1.0f and whose other entries are
+        exactly 0 in fp32, so `(hard * length).sum(-1)` equals the gather below bit for bit."""
         if gumbels is None:
-            hard = F.gumbel_softmax(grid_embed, hard=True)
-        else:       # the statements of torch.nn.functional.gumbel_softmax(tau=1, hard=True) on given noise
-            y_soft = (grid_embed + gumbels).softmax(-1)
-            index = y_soft.max(-1, keepdim=True)[1]
-            y_hard = torch.zeros_like(grid_embed, memory_format=torch.legacy_contiguous_format).scatter_(-1, index, 1.0)
-            hard = y_hard - y_soft.detach() + y_soft
-        pred_dist = (hard * grid_length).sum(-1).detach()
-        grid_embed = grid_embed - grid_embed.max(-1, keepdims=True)[0]
-        exp_embed = torch.exp(grid_embed)
-        exp_whole = exp_embed.sum(-1)
-        next_ind = (grid_length > pred_dist.unsqueeze(-1)).float()
-        prob_next = (exp_embed * next_ind).sum(-1) / exp_whole
-        prob_next = 1 - prob_next.detach() + prob_next
-        return prob_next * pred_dist
+            gumbels = -torch.empty_like(grid_embed, memory_format=torch.legacy_contiguous_format).exponential_().log()
+        pick = (grid_embed + gumbels).softmax(-1).max(-1, keepdim=True)[1]
+        sampled = grid_length.gather(-1, pick).squeeze(-1).detach()
+        weight = torch.exp(grid_embed - grid_embed.max(-1, keepdim=True)[0])
+        beyond = (weight * (grid_length > sampled.unsqueeze(-1)).float()).sum(-1) / weight.sum(-1)
+        return (1 - beyond.detach() + beyond) * sampled
 
     @staticmethod
     def _sigma_volume(level, bs, frames, heights, bev_h, bev_w):
