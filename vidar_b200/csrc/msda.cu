@@ -137,9 +137,9 @@ __device__ __forceinline__ void epi_decode(const MsdaParams& p, long long item0,
   const float e = expf(logit - warp_max(logit));
   aw = __fdiv_rn(e, warp_sum(e));
   const float2 off = __ldg(reinterpret_cast<const float2*>(loc0) + s);
-  const long long bq = item0 / p.H;
+  const unsigned bq = (unsigned)item0 / (unsigned)p.H;      // items < 2^31 on the vector path (vec_ok)
   const int z = (s % p.P) % p.D;
-  const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) + bq * p.D + z);
+  const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) + (size_t)bq * p.D + z);
   xy.x = __fadd_rn(__fdiv_rn(off.x, Wl), r.x);
   xy.y = __fadd_rn(__fdiv_rn(off.y, Hl), r.y);
 }
