@@ -51,3 +51,27 @@ def test_bad_arguments_are_reported_not_crashed():
         assert "null pointer" in str(e)
     else:
         raise AssertionError("check() must raise")
+
+
+def test_argument_validation_of_the_fused_entry_points():
+    """Shape contracts of the fused ops are checked before anything touches the device, so they can be
+    exercised on a GPU-less host: every call below must return VIDAR_E_INVALID with a message."""
+    L = _lib.lib()
+    N = None
+    cases = [
+        (L.vidar_latent_proj_in_forward, (N, N, N, N, N, N, N, 10, 64, 16, 16, N), b"embed_dims must be 128 or 256"),
+        (L.vidar_latent_proj_in_backward, (N,) * 10 + (10, 256, 20, 16, N), b"pred_height + rank"),
+        (L.vidar_latent_proj_out_forward, (N, N, N, N, N, 10, 256, 24, 8, N), b"embed_dims / pred_height"),
+        (L.vidar_latent_proj_out_backward, (N,) * 9 + (10, 256, 8, 8, N), b"rank"),
+        (L.vidar_latent_proj_in_forward, (N, N, N, N, N, N, N, 10, 256, 16, 16, N), b"null pointer"),
+        (L.vidar_msda_sca_forward, (N,) * 7 + (1, 10, 8, 32, 1, 5, 4, 4, N), b"null pointer"),
+        (L.vidar_ray_gumbel_forward, (N,) * 8 + (5, 1, 4, 4, 4, 0, 1.0, N), b"bad sizes"),
+        (L.vidar_ray_gumbel_backward, (N,) * 9 + (5, 1, 4, 4, 4, 8, 1.0, N), b"null pointer"),
+    ]
+    for fn, args, needle in cases:
+        rc = fn(*args)
+        assert rc == 1, (fn.__name__, rc)
+        assert needle in L.vidar_last_error(), (fn.__name__, L.vidar_last_error())
+    # zero rows is a valid no-op
+    assert L.vidar_latent_proj_out_forward(N, N, N, N, N, 0, 256, 16, 16, N) == 0
+    assert L.vidar_ray_gumbel_forward(*((N,) * 8 + (0, 1, 4, 4, 4, 8, 1.0, N))) == 0
