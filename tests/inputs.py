@@ -2,14 +2,9 @@
 import numpy as np
 import torch
 
+from vidar_b200.synthetic import dvr_inputs_lidar, level_tensors  # noqa: F401  (re-exported)
+
 SCA_LEVELS = ((116, 200), (58, 100), (29, 50), (15, 25))   # 928x1600 input, strides 8..64
-
-
-def level_tensors(levels, device="cpu"):
-    shapes = torch.tensor(levels, dtype=torch.int64, device=device)
-    hw = shapes[:, 0] * shapes[:, 1]
-    lsi = torch.cat([hw.new_zeros(1), hw.cumsum(0)[:-1]])
-    return shapes, lsi
 
 
 def msda_inputs(B, Q, H, C, levels, P, seed=0, mode="local", device="cpu", dtype=torch.float32):
@@ -46,28 +41,6 @@ def dvr_inputs_cfg1(seed=0, integer_origin=True, M=1000, pad=16):
     if pad:
         points[0, -pad:] = np.nan
         tindex[0, -pad:] = -1
-    return sigma, origin, points, tindex
-
-
-def dvr_inputs_lidar(M=30000, T=3, grid=(16, 200, 200), seed=0, N=1, pad=0):
-    """BASELINE.json configs[2]: sigma [N,T,16,200,200] = softplus(N(0,1)), origin ~ grid centre,
-    32-beam LiDAR-like endpoints, range U(2,70) m at 0.512 m/voxel."""
-    rng = np.random.default_rng(seed)
-    Z, Y, X = grid
-    sigma = np.log1p(np.exp(rng.standard_normal((N, T, Z, Y, X)))).astype(np.float32)
-    origin = (np.array([X / 2, Y / 2, Z * 5.0 / 8.0]) + rng.normal(0, 0.5, (N, T, 3))).astype(np.float32)
-    beams = np.deg2rad(np.linspace(-30, 10, 32))
-    elev = beams[rng.integers(0, 32, (N, M))]
-    azim = rng.uniform(-np.pi, np.pi, (N, M))
-    rng_m = rng.uniform(2, 70, (N, M)) / 0.512
-    tindex = (np.arange(M) * T // M).astype(np.float32)[None].repeat(N, 0)
-    d = np.stack([np.cos(elev) * np.cos(azim), np.cos(elev) * np.sin(azim),
-                  np.sin(elev) * (Z / 8.0) / (X / 102.4)], -1)  # z voxels are 0.5 m, x/y 0.512 m
-    o_per_ray = np.take_along_axis(origin, tindex.astype(np.int64)[..., None].repeat(3, -1), 1)
-    points = (o_per_ray + d * rng_m[..., None]).astype(np.float32)
-    if pad:
-        points[:, -pad:] = np.nan
-        tindex[:, -pad:] = -1
     return sigma, origin, points, tindex
 
 

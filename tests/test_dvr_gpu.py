@@ -190,3 +190,51 @@ def test_all_padded_and_single_ray(cuda):
     pred1, gt1, _ = render.dvr.render(s, o, p[:, :1].contiguous(), t[:, :1].contiguous(), "l2")
     rp, rg, _ = dvr_ref.render(sigma, origin, points[:, :1], tindex[:, :1], "l2")
     _close(pred1, rp, "single ray", rtol=1e-5)
+
+
+def test_warp_per_ray_voxel_mismatch_rate(cuda):
+    """The warp-per-ray kernels take crossing times from fma(i, tDelta, tMax0) and the rounded path
+    voxel from round(fma(last, d, v0)) (csrc/dvr.cu header): a branch decision can differ from the
+    serial reference's only on near-exact ties.  Randomised rays from integer, half-integer and generic
+    origins -- the tie-prone cases -- against the C oracle: a different voxel shows up as a pred
+    difference far above 1e-12; the count must be zero at the ray-caster tolerance."""
+    rng = np.random.default_rng(123)
+    Z, Y, X, M = 8, 50, 50, 6000
+    sigma = rng.uniform(0, 1, (1, 3, Z, Y, X)).astype(np.float32)
+    origin = np.array([[[25.0, 25.0, 4.0], [24.5, 25.5, 3.5], [24.37, 25.61, 3.52]]], np.float32)
+    points = (rng.uniform(0, 1, (1, M, 3)) * np.array([60, 60, 10]) - np.array([5, 5, 1])).astype(np.float32)
+    points[0, ::7] = np.round(points[0, ::7])               # axis-aligned-ish / lattice end points
+    points[0, ::11] = np.round(points[0, ::11] * 2) / 2
+    tindex = rng.integers(0, 3, (1, M)).astype(np.float32)
+    s, o, p, t = _t(cuda, sigma, origin, points, tindex)
+    bad = 0
+    for phase in ("test", "train"):
+        rp, rg = dvr_ref.render_forward(sigma, origin, points, tindex, None, phase)
+        pred, gt = render.dvr.render_forward(s, o, p, t, [3, Z, Y, X], phase)
+        a = pred.cpu().numpy()
+        assert ((a == -1) == (rp == -1)).all()
+        bad += int((np.abs(a - rp) > 1e-5 * np.maximum(1.0, np.abs(rp))).sum())
+    rp, rg, rgrad = dvr_ref.render(sigma, origin, points, tindex, "l1")
+    pred, gt, grad = render.dvr.render(s, o, p, t, "l1")
+    bad += int((np.abs(pred.cpu().numpy() - rp) > 1e-5 * np.maximum(1.0, np.abs(rp))).sum())
+    assert bad == 0, f"{bad} rays took a different voxel sequence than the reference"
+    _close(grad, rgrad, "grad_sigma")
+
+
+def test_large_grid_needs_shared_memory_opt_in_for_both_kernels(cuda):
+    """X+Y+Z > ~600: the warp-per-ray kernels need more than 48 KB of dynamic shared memory; the
+    opt-in must be applied to render_forward's AND render's instantiation (same function-pointer type)."""
+    rng = np.random.default_rng(5)
+    Z, Y, X, M = 8, 420, 400, 1500
+    sigma = rng.uniform(0, 0.05, (1, 1, Z, Y, X)).astype(np.float32)
+    origin = np.array([[[200.3, 210.7, 4.2]]], np.float32)
+    points = (rng.uniform(0, 1, (1, M, 3)) * np.array([X, Y, Z])).astype(np.float32)
+    tindex = np.zeros((1, M), np.float32)
+    s, o, p, t = _t(cuda, sigma, origin, points, tindex)
+    rp, rg = dvr_ref.render_forward(sigma, origin, points, tindex, None, "train")
+    pred, gt = render.dvr.render_forward(s, o, p, t, [1, Z, Y, X], "train")
+    _close(pred, rp, "pred (large grid, render_forward)", rtol=1e-5)
+    rp2, rg2, rgrad = dvr_ref.render(sigma, origin, points, tindex, "l2")
+    pred2, gt2, grad = render.dvr.render(s, o, p, t, "l2")
+    _close(pred2, rp2, "pred (large grid, render)", rtol=1e-5)
+    _close(grad, rgrad, "grad_sigma (large grid)")

@@ -87,3 +87,17 @@ def require_cuda(**tensors):
             raise RuntimeError(f"{name} must be a CUDA tensor")
         if not t.is_contiguous():
             raise RuntimeError(f"{name} must be contiguous")
+
+
+def require_aligned(nbytes=16, **tensors):
+    """The vector kernels use 16-byte loads / reductions (ld.global.v4, red.global.v4): a contiguous
+    view with an odd storage offset would fault with a misaligned address."""
+    for name, t in tensors.items():
+        if t is not None and t.numel() and t.data_ptr() % nbytes:
+            raise RuntimeError(f"{name} must be {nbytes}-byte aligned (data_ptr {t.data_ptr():#x}); "
+                               f"pass a fresh tensor, e.g. `{name}.clone()`")
+
+
+def aligned(t, nbytes=16):
+    """t itself when its storage is `nbytes`-aligned, else a (fresh, aligned) copy."""
+    return t if (t.numel() == 0 or t.data_ptr() % nbytes == 0) else t.clone()

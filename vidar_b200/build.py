@@ -42,7 +42,7 @@ def _digest():
     files = _sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "vidar_b200.h")]
     for f in sorted(files):
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.relpath(f, ROOT).encode())      # machine-independent
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()

@@ -8,7 +8,15 @@
 // operation order (float->int truncation of the origin, the -1:+1 / 0:+1 first-boundary
 // rule, strict-< tie order X<Y, X<Z, Y<Z else Z, the rounded "path" voxel of
 // render_forward/dvxlr, the consecutive-duplicate merge of dvxlr, termination rules),
-// so every branch decision equals the reference's.
+// so every branch decision of the thread-per-ray kernels (dvxlr family, and every ray that
+// starts outside the grid) equals the reference's.  The warp-per-ray kernels used by
+// dvr.render_forward / dvr.render compute crossing times as fma(i, tDelta, tMax0) instead of by
+// repeated addition and the rounded path voxel as round(fma(last, d, v0)): a decision can
+// differ from the reference's only when two crossing times (or a path coordinate and a .5
+// tie) agree to ~1e-13 relative -- a zero-length segment changes side, or the neighbouring
+// voxel is sampled for a zero-length interval; pred/gt agree to 1e-12 relative instead of
+// bit for bit (tests/test_dvr_gpu.py::test_warp_per_ray_voxel_mismatch_rate counts mismatches
+// against the C oracle on randomised rays).
 //
 // What is redesigned: the reference keeps five MAX_D-long fp64/int3 arrays per thread
 // (52-75 KB of local memory per ray, dvr.cu:176-179,490-494,594) and walks them three
@@ -698,13 +706,12 @@ bool warp_ray_config(const Grid& G, K kernel, int& cap, size_t& smem) {
   smem = (size_t)kWarpRaysPerBlock * cap * (2 * sizeof(double) + sizeof(int));
   if (smem > 200 * 1024) return false;
   if (smem > 48 * 1024) {
-    static thread_local size_t granted = 0;   // per kernel instantiation (template function)
-    if (granted < smem) {
-      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-      }
-      granted = smem;
+    // The opt-in is per (kernel, device) and cheap: set it on every launch that needs it.  (A cached
+    // flag keyed only on the kernel's *type* is shared by instantiations with the same signature and
+    // is wrong on a second device.)
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
     }
   }
   return true;

@@ -48,6 +48,7 @@ def ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
             raise RuntimeError(f"{name} must be float32 (got {t.dtype})")
     B, K, H, Cd, L, Q, P = _dims(value, sampling_locations, attention_weights,
                                  value_spatial_shapes, value_level_start_index)
+    _lib.require_aligned(value=value, sampling_locations=sampling_locations, attention_weights=attention_weights)
     out = torch.empty((B, Q, H * Cd), dtype=torch.float32, device=value.device)
     if out.numel() == 0:
         return out
@@ -83,6 +84,9 @@ def ms_deform_attn_backward(value, value_spatial_shapes, value_level_start_index
         raise RuntimeError("grad_* tensors must have the shapes of value / sampling_locations / attention_weights")
     if grad_output.numel() == 0:
         return None
+    _lib.require_aligned(value=value, sampling_locations=sampling_locations, attention_weights=attention_weights,
+                         grad_output=grad_output, grad_value=grad_value, grad_sampling_loc=grad_sampling_loc,
+                         grad_attn_weight=grad_attn_weight)
     with torch.cuda.device(value.device):
         _lib.check(_lib.lib().vidar_msda_backward(
             _lib.ptr(value), _lib.ptr(value_spatial_shapes), _lib.ptr(value_level_start_index),
@@ -118,9 +122,9 @@ class MultiScaleDeformableAttnFunction_fp32(Function):
                 sampling_locations, attention_weights, im2col_step):
         ctx.im2col_step = im2col_step
         ctx.in_dtypes = (value.dtype, sampling_locations.dtype, attention_weights.dtype)
-        value = value.float().contiguous()
-        sampling_locations = sampling_locations.float().contiguous()
-        attention_weights = attention_weights.float().contiguous()
+        value = _lib.aligned(value.float().contiguous())
+        sampling_locations = _lib.aligned(sampling_locations.float().contiguous())
+        attention_weights = _lib.aligned(attention_weights.float().contiguous())
         value_spatial_shapes = value_spatial_shapes.contiguous()
         value_level_start_index = value_level_start_index.contiguous()
         output = ext_module.ms_deform_attn_forward(
@@ -140,7 +144,7 @@ class MultiScaleDeformableAttnFunction_fp32(Function):
         grad_attn_weight = torch.empty_like(attention_weights)
         ext_module.ms_deform_attn_backward(
             value, value_spatial_shapes, value_level_start_index, sampling_locations,
-            attention_weights, grad_output.float().contiguous(), grad_value, grad_sampling_loc,
+            attention_weights, _lib.aligned(grad_output.float().contiguous()), grad_value, grad_sampling_loc,
             grad_attn_weight, im2col_step=ctx.im2col_step)
         dv, dl, da = ctx.in_dtypes
         return grad_value.to(dv), None, None, grad_sampling_loc.to(dl), grad_attn_weight.to(da), None
@@ -176,18 +180,31 @@ class MSDeformAttn3DFusedFunction(Function):
 
     @staticmethod
     def forward(ctx, value, spatial_shapes, level_start_index, reference_points, offsets, logits):
-        _lib.require_cuda(value=value.contiguous(), offsets=offsets.contiguous())
-        value = value.float().contiguous()
-        ref = reference_points.float().contiguous()
-        offsets = offsets.float().contiguous()
-        logits = logits.float().contiguous()
+        value = _lib.aligned(value.float().contiguous())
+        ref = _lib.aligned(reference_points.float().contiguous())
+        offsets = _lib.aligned(offsets.float().contiguous())
+        logits = _lib.aligned(logits.float().contiguous())
         spatial_shapes = spatial_shapes.contiguous()
         level_start_index = level_start_index.contiguous()
+        _lib.require_cuda(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                          reference_points=ref, offsets=offsets, logits=logits)
+        if value.dim() != 4:
+            raise RuntimeError(f"value must be [bs, num_keys, num_heads, dim], got {tuple(value.shape)}")
+        if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+            raise RuntimeError("spatial_shapes / level_start_index must be int64 tensors")
         B, K, H, C = value.shape
+        if ref.dim() != 4 or ref.shape[0] != B or ref.shape[-1] != 2:
+            raise RuntimeError(f"reference_points must be [bs, num_queries, num_Z_anchors, 2], got {tuple(ref.shape)}")
         Q, D = ref.shape[1], ref.shape[2]
+        if spatial_shapes.dim() != 2 or spatial_shapes.shape[1] != 2:
+            raise RuntimeError("spatial_shapes must be [num_levels, 2]")
         L = spatial_shapes.shape[0]
+        if level_start_index.numel() != L:
+            raise RuntimeError("level_start_index must be [num_levels]")
+        if B * Q * H * L == 0 or offsets.numel() % (B * Q * H * L * 2):
+            raise RuntimeError("offsets must be [bs, num_queries, num_heads, num_levels, num_points, 2]")
         P = offsets.numel() // (B * Q * H * L * 2)
-        if tuple(ref.shape) != (B, Q, D, 2) or logits.numel() != B * Q * H * L * P:
+        if logits.numel() != B * Q * H * L * P:
             raise RuntimeError("reference_points must be [B,Q,D,2], offsets [B,Q,H,L,P,2], logits [B,Q,H,L*P]")
         out = torch.empty((B, Q, H * C), dtype=torch.float32, device=value.device)
         with torch.cuda.device(value.device):
@@ -203,7 +220,7 @@ class MSDeformAttn3DFusedFunction(Function):
     def backward(ctx, grad_output):
         value, spatial_shapes, level_start_index, ref, offsets, logits = ctx.saved_tensors
         B, K, H, C, L, Q, P, D = ctx.dims
-        grad_output = grad_output.float().contiguous()
+        grad_output = _lib.aligned(grad_output.float().contiguous())
         grad_value = torch.zeros_like(value)
         grad_offsets = torch.empty_like(offsets)
         grad_logits = torch.empty_like(logits)
