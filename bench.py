@@ -49,44 +49,14 @@ LR_CFG = dict(type="LatentRendering", embed_dims=EMBED, num_pred_fcs=0, pred_hei
 # synthetic inputs
 # ------------------------------------------------------------------------------------------
 def sca_like_inputs(device, cams=NUM_CAMS, Q=BEV_Q, seed=0):
-    """Every camera sees a fan of Q pillars of its own frustum: perspective projection of a
-    200x200 polar BEV patch with 4 Z-anchors (-4,-2,0,2 m, camera at 1.5 m), f = 1266 px on a
-    1600x928 image, plus N(0, 4 px) learned-offset noise per (head, level, point).  Bottom
-    anchors of near pillars fall outside the image, as in the real rig."""
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    L, P, H = len(LEVELS), POINTS, HEADS
-    K = sum(h * w for h, w in LEVELS)
-    n = int(math.isqrt(Q))
-    assert n * n == Q
-    iy, ix = torch.meshgrid(torch.arange(n), torch.arange(n), indexing="ij")
-    depth = 2.0 + 49.0 * (iy.reshape(-1).float() + 0.5) / n               # 2 .. 51 m
-    ang = ((ix.reshape(-1).float() + 0.5) / n - 0.5) * math.radians(60.0)
-    u = 0.5 + torch.tan(ang) * 1266.0 / 1600.0
-    zs = torch.tensor([-4.0, -2.0, 0.0, 2.0])
-    v = (491.0 + 1266.0 * (1.5 - zs)[None, :] / depth[:, None]) / 928.0    # [Q, 4]
-    ref = torch.stack([u[:, None].expand(-1, 4), v], -1)                   # [Q, 4(z), 2]
-    ref = ref[None].expand(cams, -1, -1, -1).clone()
-    ref += 0.01 * torch.randn(cams, 1, 1, 2, generator=g)                  # per-camera jitter
-    ref = ref.to(device)
-    wh = torch.tensor([[w, h] for h, w in LEVELS], dtype=torch.float32, device=device)
-    dg = torch.Generator(device=device).manual_seed(seed + 1)
-    off = 4.0 * torch.randn(cams, Q, H, L, P, 2, device=device, generator=dg) / wh.view(1, 1, 1, L, 1, 2)
-    # point p = j*4 + z uses Z-anchor z (spatial_cross_attention.py:356-371)
-    loc = off.view(cams, Q, H, L, P // 4, 4, 2) + ref.view(cams, Q, 1, 1, 1, 4, 2)
-    loc = loc.view(cams, Q, H, L, P, 2).contiguous()
-    attn = torch.softmax(torch.randn(cams, Q, H, L * P, device=device, generator=dg), -1)
-    attn = attn.view(cams, Q, H, L, P).contiguous()
-    value = torch.randn(cams, K, H, HEAD_DIM, device=device, generator=dg)
-    grad_out = torch.randn(cams, Q, H * HEAD_DIM, device=device, generator=dg)
-    shapes = torch.tensor(LEVELS, dtype=torch.int64, device=device)
-    hw = shapes[:, 0] * shapes[:, 1]
-    lsi = torch.cat([hw.new_zeros(1), hw.cumsum(0)[:-1]])
-    return dict(value=value, shapes=shapes, lsi=lsi, loc=loc, attn=attn, grad_out=grad_out)
+    from vidar_b200 import synthetic
+    return synthetic.sca_like_inputs(device, cams=cams, Q=Q, seed=seed, levels=LEVELS, heads=HEADS,
+                                     head_dim=HEAD_DIM, points=POINTS)
 
 
 def ray_inputs():
-    from tests.inputs import dvr_inputs_lidar
-    return dvr_inputs_lidar(M=RAYS, T=FRAMES, grid=GRID, seed=0)
+    from vidar_b200 import synthetic
+    return synthetic.dvr_inputs_lidar(M=RAYS, T=FRAMES, grid=GRID, seed=0)
 
 
 # ------------------------------------------------------------------------------------------
@@ -169,10 +139,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def bench_config(world):
+    """The `config` object of the JSON line -- identical for the GPU arm and the reference arm."""
+    return {"workload": WORKLOAD,
+            "l2_policy": "inputs larger than L2 (1.4 GB of MSDA operands per step)",
+            "sharding": ("cameras sharded over ranks as (camera, interleaved 64-row sub-slice) units "
+                         "(vidar_b200.sca.unit_plan); per step: reduce-scatter of the partial BEV slot grids "
+                         "(41 MB) + ONE all-gather of the BEV grid, backward = all-gather of the row gradients; "
+                         "rays split over ranks, one all-reduce of both ray stages' grad_sigma (2 x 7.7 MB); "
+                         "LatentRendering: BEV rows/cells split over ranks") if world > 1 else "single GPU"}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
-    from vidar_b200 import _lib, msda, ray_head, render, sharding
+    from vidar_b200 import _lib, ray_head, render, sca, sharding
     from vidar_b200.registry import build_attention
     import vidar_b200.modules  # noqa: F401  (registers LatentRendering)
 
@@ -183,22 +164,32 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    grp = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        grp = dist.group.WORLD
 
-    # ---- device-resident inputs (this rank's shard)
+    # ---- device-resident inputs (this rank's shard): the product's own unit plan decides who owns what
     full = sca_like_inputs(dev)
-    segs = sharding.shard_rows(rank, world, NUM_CAMS, BEV_Q)
-    cam_groups = sharding.camera_groups(world, NUM_CAMS, BEV_Q, rank) if world > 1 else {}
-    my_cams = sorted({c for c, _, _ in segs})
-    seg_in = []
-    for c, q0, q1 in segs:
-        seg_in.append(dict(cam=c, value=full["value"][c:c + 1],
-                           loc=full["loc"][c:c + 1, q0:q1].contiguous(),
-                           attn=full["attn"][c:c + 1, q0:q1].contiguous(),
-                           grad_out=full["grad_out"][c:c + 1, q0:q1].contiguous()))
-    rows = sum(q1 - q0 for _, q0, q1 in segs)
+    plan = sca.unit_plan(world, rank, NUM_CAMS)
+    cam_groups = sca.camera_groups(world, NUM_CAMS, rank) if world > 1 else {}
+    groups = []
+    for cam0, ncl, S, lo, hi in plan:
+        sl = slice(cam0, cam0 + ncl)
+        groups.append(dict(plan=(cam0, ncl, S, lo, hi), value=full["value"][sl].contiguous(),
+                           loc=full["loc"][sl].contiguous(), attn=full["attn"][sl].contiguous()))
+    nblk = -(-BEV_Q // sca.SLICE_ROWS)
+    rows = 0                      # (camera, query) rows this rank samples
+    for cam0, ncl, S, lo, hi in plan:
+        per_cam = sum(min(sca.SLICE_ROWS, BEV_Q - blk * sca.SLICE_ROWS) for blk in range(nblk) if lo <= blk % S < hi)
+        rows += ncl * per_cam
+    my_cams = sca.plan_cameras(plan)
     shapes, lsi = full["shapes"], full["lsi"]
+    # the gradient of the BEV grid (one per pillar, as in the model) and 1 / #cameras (every camera sees every
+    # pillar in the dense cfg2 shape): SpatialCrossAttention's normalisation (spatial_cross_attention.py:168-171)
+    gg = torch.Generator(device=dev).manual_seed(11)
+    grad_bev = torch.randn(BEV_Q, HEADS * HEAD_DIM, device=dev, generator=gg)
+    inv_count = torch.full((1, BEV_Q), 1.0 / NUM_CAMS, device=dev)
     sigma_np, origin_np, points_np, tindex_np = ray_inputs()
     r0, r1 = rank * RAYS // world, (rank + 1) * RAYS // world
     sigma = torch.from_numpy(sigma_np).to(dev)
@@ -213,45 +204,45 @@ def run_ours(args):
     torch.manual_seed(0)
     latent = build_attention(LR_CFG).to(dev)
     if world > 1:
-        latent.process_group = dist.group.WORLD      # shard the BEV cells of the latent-rendering core
+        latent.process_group = grp      # shard the BEV cells of the latent-rendering core
     lg = torch.Generator(device=dev).manual_seed(7)
     embed = torch.randn(1, GRID[1], GRID[2], EMBED, device=dev, generator=lg)
     grad_embed = torch.randn(1, GRID[1], GRID[2], EMBED, device=dev, generator=lg)
-    grad_value = {c: torch.zeros(1, sum(h * w for h, w in LEVELS), HEADS, HEAD_DIM, device=dev) for c in my_cams}
-    slots = torch.zeros(BEV_Q, HEADS * HEAD_DIM, device=dev)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     names = ["msda_fwd", "msda_bwd", "latent_render", "ray_ce", "render"]
     ray_grads = torch.empty((2,) + tuple(sigma.shape[1:]), device=dev) if world > 1 else None
     marks = []
 
+    def msda_stage(gs, group, world_):
+        """SpatialCrossAttention's sampling stage through the product API: rows of this rank's (camera,
+        sub-slice) units reduced straight into the BEV slots (vidar_b200.sca.MSDARowsFunction), then the
+        exchange on the BEV grid.  -> (bev [Q, 256] replicated, leaves)"""
+        leaves, flat = [], []
+        for g_ in gs:
+            t = [g_["value"].detach().requires_grad_(True), g_["loc"].detach().requires_grad_(True),
+                 g_["attn"].detach().requires_grad_(True)]
+            leaves.append(t)
+            flat += t
+        slots = sca.MSDARowsFunction.apply([g_["plan"] for g_ in gs], 1, BEV_Q, shapes, lsi, None, None, inv_count, *flat)
+        bev = slots[0]
+        if world_ > 1:
+            bev = sharding.all_gather_rows(sharding.reduce_scatter_rows(bev, group), BEV_Q, group)
+        return bev, leaves
+
     def step(record):
         e = [ev() for _ in range(6)] if record else None
         if record:
             e[0].record()
-        outs = []
-        for s in seg_in:
-            outs.append(msda.ext_module.ms_deform_attn_forward(s["value"], shapes, lsi, s["loc"], s["attn"], im2col_step=64))
-        # SpatialCrossAttention's scatter-add of the per-camera rows into the BEV slots
-        # (spatial_cross_attention.py:164-166) is local; only the 41 MB BEV grid crosses NVLink.
-        slots.zero_()
-        for sgm, o in zip(segs, outs):
-            slots[sgm[1]:sgm[2]] += o[0]
-        if world > 1:
-            dist.all_reduce(slots)
+        bev, leaves = msda_stage(groups, grp, world)
         if record:
             e[1].record()
-        for c in my_cams:
-            grad_value[c].zero_()
-        grads = []
-        for s in seg_in:
-            gl = torch.empty_like(s["loc"])
-            ga = torch.empty_like(s["attn"])
-            msda.ext_module.ms_deform_attn_backward(s["value"], shapes, lsi, s["loc"], s["attn"], s["grad_out"],
-                                                    grad_value[s["cam"]], gl, ga, im2col_step=64)
-            grads.append((gl, ga))
-        for c, grp in cam_groups.items():   # a camera split over ranks: sum its partial grad_value
-            dist.all_reduce(grad_value[c], group=grp)
+        bev.backward(grad_bev)
+        for g_, t in zip(groups, leaves):   # a camera split over ranks: sum its partial grad_value
+            cam0, ncl = g_["plan"][0], g_["plan"][1]
+            for c in range(cam0, cam0 + ncl):
+                if c in cam_groups:
+                    dist.all_reduce(t[0].grad[c - cam0], group=cam_groups[c])
         if record:
             e[2].record()
         emb = embed.detach().requires_grad_(True)
@@ -275,7 +266,7 @@ def run_ours(args):
         if record:
             e[5].record()
             marks.append(e)
-        return outs, grads, pred, grad_sigma, emb.grad, ce_grad
+        return bev.detach(), leaves, pred, grad_sigma, emb.grad, ce_grad
 
     def sync():
         torch.cuda.synchronize()
@@ -294,7 +285,7 @@ def run_ours(args):
     t0, t1 = ev(), ev()
     t0.record()
     for _ in range(args.steps):
-        step(True)
+        last = step(True)
     t1.record()
     sync()
     sampler.mark_end()
@@ -319,16 +310,27 @@ def run_ours(args):
             _emit(json.dumps({"profile_only": True, "ms_per_step": ms_step, "breakdown_ms": parts}))
         return
 
+    # ---- sharded == single GPU: every rank recomputes nothing; rank-summed results are compared with an
+    #      unsharded recompute of the same step on rank 0 (outside the timed region)
+    sharded_check = None
+    if world > 1:
+        sharded_check = check_sharded(dev, rank, world, grp, last, groups, msda_stage, grad_bev, latent, embed, grad_embed,
+                                      sigma, origin, (points_np, tindex_np), shapes, lsi, cam_groups)
+
     # ---- end-to-end through the plugin API with HOST buffers (pinned), copies timed
     e2e = None
-    host_in = []
-    for s in seg_in:
-        host_in.append({k: s[k].cpu().pin_memory() for k in ("value", "loc", "attn", "grad_out")})
+    host_in = []                 # one piece per camera so that uploads, compute and downloads pipeline
+    for g_ in groups:
+        cam0, ncl, S, lo, hi = g_["plan"]
+        for cl in range(ncl):
+            host_in.append(dict(plan=(cam0 + cl, 1, S, lo, hi),
+                                **{k: g_[k][cl:cl + 1].cpu().pin_memory() for k in ("value", "loc", "attn")}))
+    h_gbev = grad_bev.cpu().pin_memory()
     h_sigma, h_origin = sigma.cpu().pin_memory(), origin.cpu().pin_memory()
     h_points, h_tindex = points.cpu().pin_memory(), tindex.cpu().pin_memory()
     h_embed, h_gembed = embed.cpu().pin_memory(), grad_embed.cpu().pin_memory()
-    h2d = sum(t.numel() * 4 for h in host_in for t in h.values()) + 4 * (
-        h_sigma.numel() + h_origin.numel() + h_points.numel() + h_tindex.numel()
+    h2d = sum(h[k].numel() * 4 for h in host_in for k in ("value", "loc", "attn")) + 4 * (
+        h_gbev.numel() + h_sigma.numel() + h_origin.numel() + h_points.numel() + h_tindex.numel()
         + h_embed.numel() + h_gembed.numel())
     # Copies and compute are pipelined on three streams (H2D / compute / D2H): while camera c
     # computes, camera c+1 is uploading and camera c-1 is downloading (PCIe is full duplex).
@@ -358,18 +360,31 @@ def run_ours(args):
     host_out = {}
 
     def e2e_step():
-        ups = [upload([h[k] for k in ("value", "loc", "attn", "grad_out")]) for h in host_in]
+        ups = [upload([h[k] for k in ("value", "loc", "attn")]) for h in host_in]
+        up_g = upload([h_gbev])
         up_r = upload([h_sigma, h_origin, h_points, h_tindex])
         up_l = upload([h_embed, h_gembed])
-        for i, (t, e_) in enumerate(ups):
+        parts_, leaves_ = [], []
+        for h, (t, e_) in zip(host_in, ups):
             s_cmp.wait_event(e_)
             for x in t:
                 x.record_stream(s_cmp)
-            v, loc, aw, go = t
+            v, loc, aw = t
             v.requires_grad_(True), loc.requires_grad_(True), aw.requires_grad_(True)
-            out = msda.MultiScaleDeformableAttnFunction_fp32.apply(v, shapes, lsi, loc, aw, 64)
-            out.backward(go)
-            download([out.detach(), v.grad, loc.grad, aw.grad], ("msda", i))
+            parts_.append(sca.MSDARowsFunction.apply([h["plan"]], 1, BEV_Q, shapes, lsi, None, None, inv_count, v, loc, aw)[0])
+            leaves_.append((h["plan"][0], v, loc, aw))
+        bev = parts_[0] if len(parts_) == 1 else torch.stack(parts_).sum(0)
+        if world > 1:
+            bev = sharding.all_gather_rows(sharding.reduce_scatter_rows(bev, grp), BEV_Q, grp)
+        download([bev.detach()], "bev")
+        (gb,), e_ = up_g
+        s_cmp.wait_event(e_)
+        gb.record_stream(s_cmp)
+        bev.backward(gb)
+        for i, (c, v, loc, aw) in enumerate(leaves_):
+            if c in cam_groups:
+                dist.all_reduce(v.grad, group=cam_groups[c])
+            download([v.grad, loc.grad, aw.grad], ("msda", i))
         (sg, og, pt, ti), e_ = up_r
         s_cmp.wait_event(e_)
         for x in (sg, og, pt, ti):
@@ -405,8 +420,9 @@ def run_ours(args):
     d2h = sum(t.numel() * 4 for ts in host_out.values() for t in ts)
     e2e = {"value": RAYS / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "api": "MultiScaleDeformableAttnFunction_fp32.apply+backward, LatentRendering module, ray_head.ray_ce, "
-                  "dvr.render; pinned host tensors in, pinned host tensors out; H2D / compute / D2H on three streams"}
+           "api": "vidar_b200.sca.MSDARowsFunction (rows -> BEV slots) + BEV-grid exchange + backward, LatentRendering "
+                  "module, ray_head.ray_ce, dvr.render; pinned host tensors in, pinned host tensors out; "
+                  "H2D / compute / D2H on three streams"}
 
     if rank != 0:
         if world > 1:
@@ -418,7 +434,7 @@ def run_ours(args):
     fwd_b, bwd_b = msda_algorithmic_bytes(rows, len(my_cams))
     dom = "msda_bwd" if parts["msda_bwd"] >= parts["msda_fwd"] else "msda_fwd"
     dom_bytes = bwd_b if dom == "msda_bwd" else fwd_b
-    n_launch = len(seg_in)
+    n_launch = len(groups)
     achieved = dom_bytes / (parts[dom] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -438,13 +454,8 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (seeded: perspective pillar fan per camera, LiDAR-like rays)",
-        "config": {"workload": WORKLOAD, "l2_policy": "inputs larger than L2 (1.4 GB of MSDA operands per step)",
-                   "sharding": "rows of (camera,query) and rays split over ranks; local scatter-add into the BEV "
-                               "slots + all_reduce(BEV grid 41 MB), one all_reduce of both ray stages' grad_sigma (2 x 7.7 MB); LatentRendering: BEV "
-                               "rows/cells split over ranks (projections and ray marching), all_reduce of the 2.56 MB "
-                               "maps between phases, all_gather of the 41 MB output / grad_embed rows"
-                   if world > 1 else "single GPU"},
-        "breakdown_ms": parts, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "config": bench_config(world),
+        "breakdown_ms": parts, "sharded_check": sharded_check, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "msda_query_samples_per_s": NUM_CAMS * BEV_Q * HEADS * len(LEVELS) * POINTS / ((parts["msda_fwd"] + parts["msda_bwd"]) * 1e-3),
     }
@@ -453,34 +464,88 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def check_sharded(dev, rank, world, grp, last, groups, msda_stage, grad_bev, latent, embed, grad_embed, sigma, origin,
+                  rays_np, shapes, lsi, cam_groups):
+    """Sharded == single GPU, checked on the lease the scaling run gets (SCALE_rNN.json carries the result).
+    The last timed step's results -- BEV grid, grad_value / grad_loc / grad_attn (summed over ranks into full
+    tensors), both ray stages' grad_sigma, LatentRendering's input gradient -- against an UNSHARDED recompute of
+    the same step on every rank (plan for world 1, all rays, no process group).  -> {name: max|a-b| / max|b|}"""
+    import torch.distributed as dist
+
+    from vidar_b200 import ray_head, render, sca
+    bev, leaves, pred, grad_sigma, gemb, ce_grad = last
+    full = sca_like_inputs(dev)
+    ref_groups = [dict(plan=sca.unit_plan(1, 0, NUM_CAMS)[0], value=full["value"], loc=full["loc"], attn=full["attn"])]
+    rbev, rleaves = msda_stage(ref_groups, None, 1)
+    rbev.backward(grad_bev)
+    rv, rl, ra = (t.grad for t in rleaves[0])
+
+    def rel(a, b):
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    out = {"bev_grid": rel(bev, rbev.detach())}
+    gv = torch.zeros_like(rv)
+    gl, ga = torch.zeros_like(rl), torch.zeros_like(ra)
+    for g_, t in zip(groups, leaves):
+        cam0, ncl = g_["plan"][0], g_["plan"][1]
+        for cl in range(ncl):
+            c = cam0 + cl
+            # a shared camera's grad_value was already summed inside its group: count it once
+            owner = c not in cam_groups or dist.get_rank(cam_groups[c]) == 0
+            if owner:
+                gv[c] += t[0].grad[cl]
+            gl[c] += t[1].grad[cl]
+            ga[c] += t[2].grad[cl]
+    for t in (gv, gl, ga):
+        dist.all_reduce(t, group=grp)
+    out["grad_value"], out["grad_sampling_loc"], out["grad_attn_weight"] = rel(gv, rv), rel(gl, rl), rel(ga, ra)
+    del full, ref_groups, rleaves, gv, gl, ga
+    # rays: all of them on this rank
+    points_np, tindex_np = rays_np
+    pts, ti = torch.from_numpy(points_np).to(dev), torch.from_numpy(tindex_np).to(dev)
+    sg = sigma[0].detach().requires_grad_(True)
+    ce, _ = ray_head.ray_ce(sg, origin[0].contiguous(), pts[0].contiguous(), ti[0].to(torch.int32).contiguous(), WAYPOINTS, 1.0)
+    ce.sum().backward()
+    _, _, rgs = render.dvr.render(sigma, origin, pts, ti, "l2")
+    out["ray_ce_grad_sigma"], out["render_grad_sigma"] = rel(ce_grad, sg.grad), rel(grad_sigma, rgs)
+    # LatentRendering: same module without the process group
+    pg, latent.process_group = latent.process_group, None
+    emb = embed.detach().requires_grad_(True)
+    latent.zero_grad(set_to_none=True)
+    ro = latent(emb)
+    ro.backward(grad_embed)
+    latent.process_group = pg
+    out["latent_grad_embed"] = rel(gemb, emb.grad)
+    worst = torch.tensor([max(out.values())], device=dev)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=grp)
+    out["max_over_ranks"] = float(worst.item())
+    out["tolerance"] = 1e-4
+    out["ok"] = bool(out["max_over_ranks"] <= 1e-4)
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # CPU arm: the reference's CPU path for MSDA (multi_scale_deformable_attn_pytorch formula) and
 # the C port of the ray-caster (the reference has no CPU ray-caster), on a bounded sample.
 # ------------------------------------------------------------------------------------------
 class CpuArm:
-    """The reference's CPU formulas for the step, on a bounded sample extrapolated to the full step.
+    """The reference's CPU formulas for the step on a bounded SAMPLE: the same fraction f of every stage's
+    units, so a sample-step is f of the job and  rays/s = f * 30000 / t_sample  (ms_per_step is the measured
+    time of the sample-step, not an extrapolation):
       MSDA fwd+bwd     torch CPU grid_sample formula (= mmcv's multi_scale_deformable_attn_pytorch, the
-                       reference's own CPU path) on ONE camera at two query counts q and 4q; the affine fit
-                       t(Q) = a + b*Q gives 6*a + 240000*b (each camera pays the cost of touching its
-                       31.6 MB value / grad_value once);
-      LatentRendering  reference formula (torch CPU) on `cells` of the 40000 BEV cells, scaled;
-      head sampler+CE  reference formula (torch CPU) on `rays` of the 30000 rays, scaled;
-      dvr.render       C/OpenMP port (oracle/dvr_ref.c) on all 30000 rays.
-    `scale` in (0, 1] shrinks the samples so that K steps fit a time budget; the number of torch threads is
-    calibrated once (more threads than ~32 is slower for these ops on many-core hosts)."""
-    Q0, CELLS0, RAYS0 = 2000, 4000, 6000
+                       reference's own CPU path), all 6 cameras, f * 40000 queries each (every camera pays the
+                       cost of touching its 31.6 MB value / grad_value);
+      LatentRendering  reference formula (torch CPU) on f * 40000 BEV cells;
+      head sampler+CE  reference formula (torch CPU) on f * 30000 rays;
+      dvr.render       C/OpenMP port (oracle/dvr_ref.c) on f * 30000 rays.
+    The number of torch threads is calibrated once (more threads than ~32 is slower for these ops on
+    many-core hosts)."""
 
     def __init__(self):
-        full = sca_like_inputs(torch.device("cpu"), cams=1, Q=BEV_Q, seed=0)
-        sl = slice(BEV_Q // 2, BEV_Q // 2 + 4 * self.Q0)
-        self.d = dict(value=full["value"], shapes=full["shapes"], lsi=full["lsi"],
-                      loc=full["loc"][:, sl].contiguous(), attn=full["attn"][:, sl].contiguous(),
-                      grad_out=full["grad_out"][:, sl].contiguous())
+        self.full = sca_like_inputs(torch.device("cpu"), cams=NUM_CAMS, Q=BEV_Q, seed=0)
         g = torch.Generator().manual_seed(3)
         mk = lambda f: f(1, GRID[1], GRID[2], GRID[0], generator=g)
         self.lat = (mk(torch.randn), mk(torch.randn), mk(torch.rand))
         self.rays = ray_inputs()
-        self.scale = 1.0
         self.threads = self._calibrate_threads()
 
     def _calibrate_threads(self):
@@ -488,22 +553,24 @@ class CpuArm:
         best, best_t = cores, None
         for n in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
             torch.set_num_threads(n)
-            self._msda(250)                       # warm
-            t = self._msda(500)
+            self._msda(250, cams=1)                       # warm
+            t = self._msda(500, cams=1)
             if best_t is None or t < best_t:
                 best, best_t = n, t
         torch.set_num_threads(best)
         return best
 
-    def _msda(self, q):
+    def _msda(self, q, cams=NUM_CAMS):
         from oracle import msda_ref
-        d = self.d
+        d = self.full
+        lo = (BEV_Q - q) // 2
         t0 = time.perf_counter()
-        v = d["value"].detach().requires_grad_(True)
-        loc = d["loc"][:, :q].detach().contiguous().requires_grad_(True)
-        aw = d["attn"][:, :q].detach().contiguous().requires_grad_(True)
-        out = msda_ref.msda_grid_sample(v, d["shapes"], loc, aw)
-        out.backward(d["grad_out"][:, :q].contiguous())
+        for c in range(cams):
+            v = d["value"][c:c + 1].detach().requires_grad_(True)
+            loc = d["loc"][c:c + 1, lo:lo + q].detach().contiguous().requires_grad_(True)
+            aw = d["attn"][c:c + 1, lo:lo + q].detach().contiguous().requires_grad_(True)
+            out = msda_ref.msda_grid_sample(v, d["shapes"], loc, aw)
+            out.backward(d["grad_out"][c:c + 1, lo:lo + q].contiguous())
         return time.perf_counter() - t0
 
     def _latent(self, cells):
@@ -513,68 +580,72 @@ class CpuArm:
         o, f = occ.detach().requires_grad_(True), feat.detach().requires_grad_(True)
         p, q = lr.latent_core(o, f, LR_GRID_NUM, 0.5, 1e-3, "sigmoid", cells=slice(0, cells), prob_map=probmap)
         (p.sum() + q.sum()).backward()
-        return (time.perf_counter() - t0) * (GRID[1] * GRID[2] / cells)
+        return time.perf_counter() - t0
 
     def _ray_ce(self, rays_n):
         from oracle import ray_head_ref as rr
         sigma, origin, points, tindex = self.rays
         t0 = time.perf_counter()
         s = torch.from_numpy(sigma[0]).requires_grad_(True)
-        tot, n = 0, 0
+        tot = 0
         for f in range(FRAMES):
             sel = np.flatnonzero(tindex[0] == f)[: max(1, rays_n // FRAMES)]
             lg, ln, vd = rr.sample_frame(s[f], torch.from_numpy(origin[0, f]), torch.from_numpy(points[0][sel]), WAYPOINTS, 1.0)
             tot = tot - torch.log_softmax(lg[vd], -1)[:, 0].sum()
-            n += len(sel)
         tot.backward()
-        return (time.perf_counter() - t0) * (RAYS / n)
+        return time.perf_counter() - t0
 
-    def sizes(self):
-        q = max(250, int(self.Q0 * self.scale))
-        return q, max(500, int(self.CELLS0 * self.scale)), max(600, int(self.RAYS0 * self.scale))
-
-    def step(self):
-        """-> (estimated seconds for the FULL step, seconds of CPU work spent, per-part estimates)."""
+    def _render(self, rays_n):
         from oracle import dvr_ref
-        q, cells, rays_n = self.sizes()
-        t00 = time.perf_counter()
-        ts, tl = self._msda(q), self._msda(4 * q)
-        b = max(tl - ts, 0.0) / (3 * q)
-        a = max(ts - b * q, 0.0)
-        parts = {"msda": NUM_CAMS * a + NUM_CAMS * BEV_Q * b, "latent_render": self._latent(cells),
-                 "ray_ce": self._ray_ce(rays_n)}
+        sigma, origin, points, tindex = self.rays
         t0 = time.perf_counter()
-        dvr_ref.render(*self.rays, "l2")
-        parts["dvr_render"] = time.perf_counter() - t0
-        return sum(parts.values()), time.perf_counter() - t00, parts
+        dvr_ref.render(sigma, origin, np.ascontiguousarray(points[:, :rays_n]), np.ascontiguousarray(tindex[:, :rays_n]), "l2")
+        return time.perf_counter() - t0
 
-    def run(self, steps, warmup, budget_s):
-        """`warmup` untimed + `steps` timed sample-steps within about `budget_s` seconds of CPU work."""
-        _, spent, _ = self.step()                      # calibration step at full sample size (untimed)
-        self.scale = min(1.0, max(0.05, budget_s / max(steps + warmup, 1) / max(spent, 1e-6)))
+    def step(self, f):
+        """One pass over fraction f of every stage -> (seconds, per-stage seconds)."""
+        parts = {"msda": self._msda(max(8, int(BEV_Q * f))), "latent_render": self._latent(max(8, int(GRID[1] * GRID[2] * f))),
+                 "ray_ce": self._ray_ce(max(FRAMES, int(RAYS * f))), "dvr_render": self._render(max(1, int(RAYS * f)))}
+        return sum(parts.values()), parts
+
+    def run(self, steps, warmup, budget_s, full_step=False):
+        """`warmup` untimed + `steps` timed sample-steps within about `budget_s` seconds of CPU work.
+        -> dict(f, seconds per sample-step (list), per-stage seconds, optional measured full step)."""
+        self.step(0.01)                                                # first touch of every buffer / code path
+        t1, _ = self.step(0.02)                                        # two-point calibration t(f) = a + b f
+        t2, _ = self.step(0.08)
+        b = max((t2 - t1) / 0.06, 1e-6)
+        a = max(t1 - 0.02 * b, 0.0)
+        per_step = budget_s / max(steps + warmup, 1)
+        f = float(min(1.0, max(0.02, (per_step - a) / b)))
         for _ in range(max(warmup - 1, 0)):
-            self.step()
-        est = [self.step() for _ in range(steps)]
-        return est
+            self.step(f)
+        res = [self.step(f) for _ in range(steps)]
+        out = {"f": f, "t": [r[0] for r in res], "parts": {k: float(np.mean([r[1][k] for r in res])) for k in res[0][1]}}
+        if full_step:
+            out["full_step_s"] = self.step(1.0)[0]
+        return out
 
-    def describe(self, est):
+    def describe(self, r):
         from oracle import dvr_ref
-        q, cells, rays_n = self.sizes()
-        parts = {k: float(np.mean([e[2][k] for e in est])) for k in est[0][2]}
-        return (f"per step {np.mean([e[1] for e in est]):.1f} s of CPU work on {self.threads} torch threads / "
-                f"{dvr_ref.num_threads()} OpenMP threads: MSDA fwd+bwd (torch CPU grid_sample formula = the reference's CPU "
-                f"path) on 1 camera at {q} and {4 * q} queries, affine fit -> 6 cams x 40000 queries; LatentRendering core "
-                f"(reference formula) on {cells}/40000 cells, scaled; head ray sampler+CE (reference formula) on "
-                f"{rays_n}/30000 rays, scaled; C/OpenMP port of dvr.render on all 30000 rays.  Full-step estimates (s): "
-                + ", ".join(f"{k}={v:.2f}" for k, v in parts.items()))
+        f = r["f"]
+        txt = (f"each step = fraction f={f:.3f} of every stage on {self.threads} torch threads / {dvr_ref.num_threads()} OpenMP "
+               f"threads: MSDA fwd+bwd (torch CPU grid_sample formula = the reference's CPU path) 6 cameras x {int(BEV_Q * f)} "
+               f"queries; LatentRendering core (reference formula) {int(GRID[1] * GRID[2] * f)} cells; head ray sampler+CE "
+               f"(reference formula) {int(RAYS * f)} rays; C/OpenMP port of dvr.render {int(RAYS * f)} rays.  Mean seconds per "
+               "sample-step by stage: " + ", ".join(f"{k}={v:.2f}" for k, v in r["parts"].items())
+               + f"; rays/s = f*{RAYS}/t_sample")
+        if "full_step_s" in r:
+            txt += f"; ONE full-size step (f=1) measured afterwards: {r['full_step_s']:.1f} s = {RAYS / r['full_step_s']:.0f} rays/s"
+        return txt
 
 
-def cpu_baseline(sample_only=False, steps=2, warmup=1, budget_s=25.0):
+def cpu_baseline(sample_only=False, steps=2, warmup=1, budget_s=20.0):
     arm = CpuArm()
-    est = arm.run(steps, warmup, budget_s)
-    full_s = float(np.mean([e[0] for e in est]))
-    return {"value": RAYS / full_s, "unit": "rays/s", "cores": arm.threads, "kind": "port",
-            "est_ms_per_step": full_s * 1e3, "sample": arm.describe(est)}
+    r = arm.run(steps, warmup, budget_s)
+    t = float(np.mean(r["t"]))
+    return {"value": r["f"] * RAYS / t, "unit": "rays/s", "cores": arm.threads, "kind": "port", "estimated": r["f"] < 1.0,
+            "sample_fraction": r["f"], "sample_ms_per_step": t * 1e3, "sample": arm.describe(r)}
 
 
 def run_reference(args):
@@ -582,18 +653,24 @@ def run_reference(args):
     if rank != 0:
         return
     arm = CpuArm()
-    est = arm.run(args.steps, args.warmup, budget_s=150.0)      # the whole run stays within a few minutes
-    full_s = float(np.mean([e[0] for e in est]))
-    value = RAYS / full_s
-    sample = arm.describe(est)
-    _emit(json.dumps({
+    # the sampled steps stay within ~2 minutes; one honest full-size step is measured after them
+    r = arm.run(args.steps, args.warmup, budget_s=110.0, full_step=os.environ.get("VIDAR_REF_FULL_STEP", "1") == "1")
+    t = float(np.mean(r["t"]))
+    value = r["f"] * RAYS / t
+    sample = arm.describe(r)
+    line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_s * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator as the GPU arm)",
-        "config": {"workload": WORKLOAD},
+        "config": bench_config(args.gpus), "estimated": r["f"] < 1.0, "sample_fraction": r["f"],
+        "note": "ms_per_step is the measured time of one SAMPLE step (fraction f of the job); value = f*30000 rays / that time",
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": arm.threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if "full_step_s" in r:
+        line["full_step_measured_ms"] = r["full_step_s"] * 1e3
+        line["full_step_rays_per_s"] = RAYS / r["full_step_s"]
+    _emit(json.dumps(line))
 
 
 def _emit(line):

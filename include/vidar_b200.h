@@ -101,6 +101,50 @@ int vidar_msda_sca_backward(const float* value, const int64_t* spatial_shapes,
                             float* grad_value, float* grad_offsets, float* grad_logits,
                             int B, int K, int H, int C, int L, int Q, int P, int D, void* stream);
 
+/* Row-indirect variants: SpatialCrossAttention's rebatch / scatter-add (spatial_cross_attention.py:135-172)
+ * folded into the op.  A row is entry j of camera c's visible-pillar list:
+ *   idx        [cams, Qd] int32   pillar of row j (ascending; entries >= count[c] unused), NULL: row j = pillar j
+ *   count      [cams]     int32   live rows per camera, on the DEVICE (no host sync), NULL: all Qrows rows live
+ *   inv_count  [bs, Qd]           1 / clamp(#cameras seeing the pillar, 1)  (:168-171), NULL: 1
+ *   value      [bs*ncl, K, H, C]  the launch's cameras cam0 .. cam0+ncl-1, batch-major (n = b*ncl + camera)
+ *   slots      [bs, Qd, H*C]      caller-zeroed; every live row adds inv_count * (its head vectors) to the slot
+ *                                 of its pillar with red.global.add.v4.f32 (the reference's `slots[j, idx] += ...`
+ *                                 followed by `slots / count`)
+ * The launch covers rows j with (j / 64) % S in [s_lo, s_hi): interleaved sub-slices of a camera's list, the
+ * unit of work when cameras are sharded over ranks; S = 1, [0, 1) = every row.
+ * `rows`: sampling locations / weights given per row, [bs*ncl, Qrows, H, L, P(, 2)] -- the plain op's inputs.
+ * `sca_rows`: the fused MSDeformableAttention3D prologue of vidar_msda_sca_*, with
+ *   ref_cam [cams, bs, Qd, D, 2] (reference_points_cam as point_sampling lays it out) and offsets / logits
+ *   DENSE per pillar, [bs, Qd, H, L, P, 2] / [bs, Qd, H, L*P]: they are Linear(query) rows, equal for every
+ *   camera that sees the pillar, so they are computed once per pillar and read through idx.
+ * Backward: grad_slots [bs, Qd, H*C] is read through the same map; grad_value accumulated (caller zeroes);
+ *   rows:     grad_sampling_loc / grad_attn_weight written for the rows of this launch (caller zeroes the rest);
+ *   sca_rows: grad_offsets / grad_logits ACCUMULATED over cameras with red.global.add (caller zeroes). */
+int vidar_sca_compact(const unsigned char* bev_mask, int32_t* idx, int32_t* count, float* inv_count,
+                      int cams, int bs, int Q, int D, void* stream);
+int vidar_msda_rows_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                            const float* sampling_loc, const float* attn_weight, const int32_t* idx,
+                            const int32_t* count, const float* inv_count, float* slots, int bs, int ncl,
+                            int cam0, int K, int H, int C, int L, int Qrows, int Qd, int P, int S, int s_lo,
+                            int s_hi, void* stream);
+int vidar_msda_rows_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                             const float* sampling_loc, const float* attn_weight, const int32_t* idx,
+                             const int32_t* count, const float* inv_count, const float* grad_slots,
+                             float* grad_value, float* grad_sampling_loc, float* grad_attn_weight, int bs,
+                             int ncl, int cam0, int K, int H, int C, int L, int Qrows, int Qd, int P, int S,
+                             int s_lo, int s_hi, void* stream);
+int vidar_msda_sca_rows_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                const float* ref_cam, const float* offsets, const float* logits,
+                                const int32_t* idx, const int32_t* count, const float* inv_count, float* slots,
+                                int bs, int ncl, int cam0, int K, int H, int C, int L, int Qrows, int Qd, int P,
+                                int D, int S, int s_lo, int s_hi, void* stream);
+int vidar_msda_sca_rows_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                 const float* ref_cam, const float* offsets, const float* logits,
+                                 const int32_t* idx, const int32_t* count, const float* inv_count,
+                                 const float* grad_slots, float* grad_value, float* grad_offsets,
+                                 float* grad_logits, int bs, int ncl, int cam0, int K, int H, int C, int L,
+                                 int Qrows, int Qd, int P, int D, int S, int s_lo, int s_hi, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (ii-a) dvr / dvxlr / dvxlr_v2 voxel ray-casters
  *   sigma   [N, T, Z, Y, X]   (reference names the dims H, L, W)

@@ -76,25 +76,39 @@ def test_modules_have_no_cpu_fallback():
           spatial_shapes=c["spatial_shapes"], level_start_index=c["level_start_index"])
 
 
-def test_visible_lists_are_cached_per_mask_tensor(monkeypatch):
-    """SCA's rebatching lists are computed once per `bev_mask` tensor (the encoder passes the same
-    tensor to every layer): same object + same version -> cached; in-place edit or new tensor -> recomputed."""
-    calls = []
-    real = torch.argsort
-    monkeypatch.setattr(torch, "argsort", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
-    deform_attn._VISIBLE_CACHE.clear()
+def test_visible_lists_equal_reference_nonzero():
+    """The rebatch path's lists: per camera the reference's `nonzero()` indices, padded to the longest."""
     c = mc.sca_case()
     mask = c["bev_mask"]
-    a = deform_attn._visible_lists(mask)
-    b = deform_attn._visible_lists(mask)
-    assert len(calls) == 1 and a[0] is b[0]
-    idx, live, max_len = a
+    idx, live, max_len = deform_attn._visible_lists(mask)
     hit = mask[:, 0].sum(-1) > 0
     for cam in range(mask.shape[0]):
         want = hit[cam].nonzero().squeeze(-1)                      # the reference's index_query_per_img
         assert torch.equal(idx[cam][live[cam]], want)
     assert max_len == int(hit.sum(-1).max())
-    mask[0, 0, 0, 0] = ~mask[0, 0, 0, 0]                           # in-place change bumps the version
-    deform_attn._visible_lists(mask)
-    deform_attn._visible_lists(mask.clone())
-    assert len(calls) == 3
+
+
+def test_unit_plan_partitions_every_row_exactly_once():
+    """Camera sharding (vidar_b200/sca.py): over all ranks the (camera, 64-row block) units are covered
+    exactly once, shares are equal, and a rank touches at most two partial cameras."""
+    from vidar_b200.sca import SLICE_ROWS, plan_cameras, unit_plan
+    cams, Q = 6, 1000
+    nblk = -(-Q // SLICE_ROWS)
+    for world in (1, 2, 3, 4, 5, 6, 8, 12):
+        seen = {}
+        sizes = []
+        for rank in range(world):
+            plan = unit_plan(world, rank, cams)
+            units = 0
+            for cam0, ncl, S, lo, hi in plan:
+                for c in range(cam0, cam0 + ncl):
+                    for blk in range(nblk):
+                        if lo <= blk % S < hi:
+                            assert (c, blk) not in seen
+                            seen[(c, blk)] = rank
+                    units += (hi - lo) * 1.0 / S
+            sizes.append(units)
+            assert len([g for g in plan if (g[3], g[4]) != (0, g[2])]) <= 2
+            assert plan_cameras(plan) == sorted(plan_cameras(plan))
+        assert len(seen) == cams * nblk
+        assert max(sizes) - min(sizes) < 1e-9

@@ -48,6 +48,7 @@ def test_sca_fused_epilogue_equals_materialised_path(cuda):
     m.load_state_dict(mc.seeded_state(m, 10))
     m.eval().to(cuda)
     assert m.deformable_attention.fuse_epilogue
+    m.fuse_rebatch = False            # the reference's rebatch data flow: MSDeformableAttention3D is called as a module
     res = []
     for fused in (True, False):
         m.deformable_attention.fuse_epilogue = fused
@@ -59,3 +60,62 @@ def test_sca_fused_epilogue_equals_materialised_path(cuda):
                                         "grad attention_weights.weight")):
         err = (a - b).abs().max().item()
         assert err <= 2e-5 * b.abs().max().item() + 1e-7, f"{w}: {err:.3e} vs {b.abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("bs", [1, 2])
+def test_sca_fused_rebatch_equals_reference_data_flow(cuda, bs):
+    """SpatialCrossAttention's default path (device-side visible lists, offsets / logits once per pillar,
+    rows reduced straight into the BEV slots: vidar_b200/sca.py) against the reference's rebatch /
+    index_add_ data flow on the same CUDA op -- output, input gradients and every parameter gradient."""
+    m = build_attention(mc.SCA_CFG)
+    m.load_state_dict(mc.seeded_state(m, 10))
+    m.eval().to(cuda)
+    assert m.fuse_rebatch
+    res = []
+    for fused in (True, False):
+        m.fuse_rebatch = fused
+        m.zero_grad(set_to_none=True)
+        out, gq, gkv = mc.run_module(m, "sca", mc.sca_case(bs=bs), device=cuda)
+        res.append([out, gq, gkv] + [p.grad.clone() for _, p in sorted(m.named_parameters())])
+    names = ["out", "grad query", "grad key/value"] + [n for n, _ in sorted(m.named_parameters())]
+    for a, b, w in zip(res[0], res[1], names):
+        err = (a - b).abs().max().item()
+        assert err <= 2e-5 * b.abs().max().item() + 1e-7, f"{w}: {err:.3e} vs {b.abs().max().item():.3e}"
+
+
+def test_sca_default_path_has_no_host_sync(cuda):
+    """Forward + backward of the default SpatialCrossAttention path never synchronises with the host
+    (the reference syncs on `nonzero()` / max_len in every layer)."""
+    m = build_attention(mc.SCA_CFG)
+    m.load_state_dict(mc.seeded_state(m, 10))
+    m.eval().to(cuda)
+    c = {k: (v.to(cuda) if torch.is_tensor(v) else v) for k, v in mc.sca_case().items()}
+    q = c["query"].clone().requires_grad_(True)
+    kv = c["key"].clone().requires_grad_(True)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        out = m(q, kv, kv, query_pos=c["query_pos"], reference_points_cam=c["reference_points_cam"],
+                bev_mask=c["bev_mask"], spatial_shapes=c["spatial_shapes"], level_start_index=c["level_start_index"])
+        out.backward(c["grad"])
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all() and torch.isfinite(q.grad).all()
+
+
+def test_compact_visible_lists_on_device(cuda):
+    from vidar_b200 import sca
+    g = torch.Generator().manual_seed(4)
+    cams, bs, Q, D = 6, 2, 5000, 4                     # > 1024 pillars: several chunks of the block scan
+    mask = torch.rand(cams, bs, Q, D, generator=g) < 0.12
+    mask[2] = False
+    mask[4] = True
+    idx, count, inv = sca.compact_visible(mask.to(cuda))
+    hit = mask[:, 0].any(-1)
+    for c in range(cams):
+        want = hit[c].nonzero().squeeze(-1)
+        assert int(count[c]) == want.numel()
+        assert torch.equal(idx[c, : want.numel()].cpu().long(), want)
+    cnt = mask.any(-1).permute(1, 2, 0).sum(-1).clamp(min=1).float()
+    assert torch.equal(inv.cpu(), 1.0 / cnt)

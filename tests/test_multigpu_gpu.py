@@ -80,3 +80,46 @@ def test_sharded_fused_module_equals_single_gpu(tmp_path):
     for single, sharded in ((res[0], res[1]), (res[2], res[3])):
         for i, (a, b) in enumerate(zip(sharded, single)):
             torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5 * float(b.abs().max()), msg=lambda m: f"tensor {i}: {m}")
+
+
+def _sca_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from tests import module_cases as mc
+    import vidar_b200.modules  # noqa: F401
+    from vidar_b200 import sharding
+    from vidar_b200.registry import build_attention
+    res = []
+    for bs in (1, 2):
+        m = build_attention(mc.SCA_CFG)
+        m.load_state_dict(mc.seeded_state(m, 10))
+        m.eval().cuda()
+        for group in (None, dist.group.WORLD):
+            m.set_process_group(group)
+            m.zero_grad(set_to_none=True)
+            o, gq, gkv = mc.run_module(m, "sca", mc.sca_case(bs=bs), device="cuda")
+            if group is not None:
+                # camera-sharded: grad wrt the image features is non-zero only for this rank's cameras
+                dist.all_reduce(gkv, group=group)
+                sharding.allreduce_partial_grads(m, group)
+            res.append([o.cpu(), gq.cpu(), gkv.cpu()] + [p.grad.cpu() for _, p in sorted(m.named_parameters())])
+    if rank == 0:
+        torch.save(res, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_camera_sharded_sca_equals_single_gpu(tmp_path, world):
+    """SpatialCrossAttention with its cameras sharded over `world` GPUs (reduce-scatter of the partial BEV
+    slots, output_proj on the rank's rows, ONE all-gather of the BEV grid) returns the single-GPU output,
+    input gradients and -- after `allreduce_partial_grads` -- parameter gradients."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    out = str(tmp_path / "sca.pt")
+    mp.spawn(_sca_worker, args=(world, 29240 + os.getpid() % 200 + world, out), nprocs=world, join=True)
+    res = torch.load(out, weights_only=False)
+    for single, sharded in ((res[0], res[1]), (res[2], res[3])):
+        for i, (a, b) in enumerate(zip(sharded, single)):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5 * float(b.abs().max()) + 1e-7, msg=lambda m_: f"tensor {i}: {m_}")

@@ -76,3 +76,52 @@ def test_sharded_equals_single_process(tmp_path, world):
     sigma, origin, points, tindex = dvr_inputs_lidar(M=400, T=2, grid=(4, 24, 24), seed=2)
     _, _, grad = dvr_ref.render(sigma, origin, points, tindex, "l2")
     np.testing.assert_allclose(got["grad_sigma"].numpy(), grad, rtol=1e-5, atol=1e-6)
+
+
+def _rows_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(3)
+    R, C = 23, 5                                    # 23 rows: uneven blocks, the last one short
+    parts = [torch.randn(R, C, generator=g, dtype=torch.float64) for _ in range(world)]
+    w = torch.randn(C, C, generator=g, dtype=torch.float64)
+    gout = torch.randn(R, C, generator=g, dtype=torch.float64)
+    lin = torch.nn.Linear(C, C, bias=False).double()
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    sharding.mark_partial(lin)
+    x = parts[rank].clone().requires_grad_(True)           # this rank's partial sum
+    rep = torch.ones(R, C, dtype=torch.float64, requires_grad=True)     # a replicated tensor consumed per rank
+    rows = sharding.reduce_scatter_rows(x * sharding.sum_grad(rep, dist.group.WORLD), dist.group.WORLD)
+    lo, hi = sharding.row_range(R, rank, world)
+    assert rows.shape[0] == hi - lo
+    full = sharding.all_gather_rows(lin(rows), R, dist.group.WORLD)
+    (full * gout).sum().backward()
+    n = sharding.allreduce_partial_grads(lin, dist.group.WORLD)
+    assert n == C * C
+    torch.save(dict(full=full.detach(), gx=x.grad, gw=lin.weight.grad, grep=rep.grad), os.path.join(tmp, f"rows{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_collectives_with_autograd(tmp_path, world):
+    """reduce_scatter_rows -> row-wise layer -> all_gather_rows equals the single-process computation:
+    output, gradient of every rank's partial sum, the summed gradient of a replicated input (sum_grad)
+    and -- after allreduce_partial_grads -- the row-wise layer's weight gradient."""
+    port = 29700 + os.getpid() % 200 + world
+    mp.spawn(_rows_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(3)
+    R, C = 23, 5
+    parts = [torch.randn(R, C, generator=g, dtype=torch.float64) for _ in range(world)]
+    w = torch.randn(C, C, generator=g, dtype=torch.float64).requires_grad_(True)
+    gout = torch.randn(R, C, generator=g, dtype=torch.float64)
+    xs = [p.clone().requires_grad_(True) for p in parts]
+    rep = torch.ones(R, C, dtype=torch.float64, requires_grad=True)
+    full = (sum(x * rep for x in xs)) @ w.t()
+    (full * gout).sum().backward()
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), f"rows{r}.pt"), weights_only=False)
+        torch.testing.assert_close(got["full"], full.detach())
+        torch.testing.assert_close(got["gx"], xs[r].grad)
+        torch.testing.assert_close(got["gw"], w.grad)
+        torch.testing.assert_close(got["grep"], rep.grad)

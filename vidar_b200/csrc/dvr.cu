@@ -13,10 +13,11 @@
 // dvr.render_forward / dvr.render compute crossing times as fma(i, tDelta, tMax0) instead of by
 // repeated addition and the rounded path voxel as round(fma(last, d, v0)): a decision can
 // differ from the reference's only when two crossing times (or a path coordinate and a .5
-// tie) agree to ~1e-13 relative -- a zero-length segment changes side, or the neighbouring
-// voxel is sampled for a zero-length interval; pred/gt agree to 1e-12 relative instead of
-// bit for bit (tests/test_dvr_gpu.py::test_warp_per_ray_voxel_mismatch_rate counts mismatches
-// against the C oracle on randomised rays).
+// tie) agree to ~1e-13 relative.  Every step is therefore checked for such a near-tie (1e-9
+// relative) and a ray that has one -- lattice-aligned origins / end points, e.g. a half-integer
+// origin puts EVERY crossing on a round() tie -- is handed to the serial code; for all other
+// rays the decisions are identical and pred/gt agree to 1e-12 relative
+// (tests/test_dvr_gpu.py::test_warp_per_ray_voxel_mismatch_rate).
 //
 // What is redesigned: the reference keeps five MAX_D-long fp64/int3 arrays per thread
 // (52-75 KB of local memory per ray, dvr.cu:176-179,490-494,594) and walks them three
@@ -491,12 +492,20 @@ render_warp_kernel(Grid G, const float* __restrict__ sigma, const float* __restr
   }
   const int N = __shfl_sync(0xffffffffu, off, 31);
   off -= nsteps;
+  // Near-tie detection.  Crossing times here are fma(i, tDelta, tMax0); the reference adds tDelta i
+  // times, so the two agree to ~1e-13 relative but not bit for bit.  That only matters where a branch
+  // decision hangs on the last bits: two axes crossing at (almost) the same parameter, or -- rounded-path
+  // variants -- a path coordinate (almost) exactly on a .5 round() tie (e.g. half-integer origins: every
+  // crossing).  Such rays are walked by the bit-faithful serial code instead.
+  constexpr double kTieEps = 1e-9;
+  bool tie = false;
   {
-    int v[3];
+    int v[3], gi[3];
     double tm[3], last = 0.0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       v[a] = v0[a] + stp[a] * ia[a];
+      gi[a] = ia[a];
       tm[a] = moves[a] ? fma((double)ia[a], tDelta[a], tMax0[a]) : DBL_MAX;
       if (ia[a] > 0) last = fmax(last, fma((double)(ia[a] - 1), tDelta[a], tMax0[a]));
     }
@@ -507,24 +516,43 @@ render_warp_kernel(Grid G, const float* __restrict__ sigma, const float* __restr
       // the reference's choice: X if tx < ty and tx < tz; Y if !(tx < ty) and ty < tz; else Z
       const int ax = (tx < ty) ? ((tx < tz) ? 0 : 2) : ((ty < tz) ? 1 : 2);
       const double tcur = ax == 0 ? tx : (ax == 1 ? ty : tz);
+      // pending crossings of the other axes (unmasked: the neighbouring slice's first crossing counts);
+      // two 0-th crossings are exact in both formulations and need no flag
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (a != ax && moves[a] && gi[a] < hi[a] && (gi[a] > 0 || gi[ax] > 0) &&
+            fabs(tm[a] - tcur) <= kTieEps * fabs(tcur))
+          tie = true;
+      }
       const bool inside = v[0] >= 0 && v[0] < G.X && v[1] >= 0 && v[1] < G.Y && v[2] >= 0 && v[2] < G.Z;
       int idx = -1;
       if (inside) {
         int px = v[0], py = v[1], pz = v[2];
         if (TR::kRounded) {   // nearest voxel to v0 + last * dir  (dvr.cu:200-212, 255-257)
-          px = (int)round(fma(last, r.dx, (double)r.vx0)); px = px < G.X ? px : G.X - 1; px = px >= 0 ? px : 0;
-          py = (int)round(fma(last, r.dy, (double)r.vy0)); py = py < G.Y ? py : G.Y - 1; py = py >= 0 ? py : 0;
-          pz = (int)round(fma(last, r.dz, (double)r.vz0)); pz = pz < G.Z ? pz : G.Z - 1; pz = pz >= 0 ? pz : 0;
+          const double cx = fma(last, r.dx, (double)r.vx0), cy = fma(last, r.dy, (double)r.vy0),
+                       cz = fma(last, r.dz, (double)r.vz0);
+          if (last > 0.0) {
+            tie = tie || fabs(fabs(cx - floor(cx)) - 0.5) <= kTieEps * fmax(1.0, fabs(cx)) ||
+                  fabs(fabs(cy - floor(cy)) - 0.5) <= kTieEps * fmax(1.0, fabs(cy)) ||
+                  fabs(fabs(cz - floor(cz)) - 0.5) <= kTieEps * fmax(1.0, fabs(cz));
+          }
+          px = (int)round(cx); px = px < G.X ? px : G.X - 1; px = px >= 0 ? px : 0;
+          py = (int)round(cy); py = py < G.Y ? py : G.Y - 1; py = py >= 0 ? py : 0;
+          pz = (int)round(cz); pz = pz < G.Z ? pz : G.Z - 1; pz = pz >= 0 ? pz : 0;
         }
         idx = (pz * G.Y + py) * G.X + px;
       }
       ts[off + sidx] = tcur;
       vxs[off + sidx] = idx;
-      if (ax == 0) { v[0] += stp[0]; tm[0] += tDelta[0]; --rem[0]; }
-      else if (ax == 1) { v[1] += stp[1]; tm[1] += tDelta[1]; --rem[1]; }
-      else { v[2] += stp[2]; tm[2] += tDelta[2]; --rem[2]; }
+      if (ax == 0) { v[0] += stp[0]; tm[0] += tDelta[0]; --rem[0]; ++gi[0]; }
+      else if (ax == 1) { v[1] += stp[1]; tm[1] += tDelta[1]; --rem[1]; ++gi[1]; }
+      else { v[2] += stp[2]; tm[2] += tDelta[2]; --rem[2]; ++gi[2]; }
       last = fmax(last, tcur);
     }
+  }
+  if (__any_sync(0xffffffffu, tie)) {
+    if (lane == 0) serial_ray<V>(G, r, sigma, pred_dist, gt_dist, grad_sigma, n, c, mode, GRAD);
+    return;
   }
   __syncwarp();
   // ---- phase 2: compositing over the records, 32 steps at a time

@@ -21,6 +21,8 @@
 // Work order: for L*P >= 32 a block is 8 consecutive queries of one (b, h) and
 // neighbouring blocks are the other heads of the same queries, so the lines a block
 // touches are neighbours in the image (L1/L2 locality).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vidar {
@@ -43,6 +45,14 @@ struct MsdaParams {
   // of the sampling_offsets Linear, `attn` the logits of the attention_weights Linear
   const float* ref;   // [B, Q, D, 2] projected Z-anchors (reference_points_cam), normalised
   int D;
+  // Row-indirect mode (IDX kernels): a row of batch element n = b*ncl + cl is entry j of camera
+  // (cam0 + cl)'s visible-pillar list; results go to / gradients come from the dense BEV slot grid.
+  const int* idx;      // [cams, Qd] pillar of row j, or nullptr (row j is pillar j)
+  const int* count;    // [cams] live rows per camera, or nullptr (all Q rows are live)
+  const float* inv;    // [bs, Qd] output scale 1 / #cameras seeing the pillar, or nullptr
+  int ncl, cam0, bs, Qd;   // cameras in this launch, first camera, batch size, pillars per batch element
+  int S, s_lo, s_hi;   // the launch covers rows with (j / 64) % S in [s_lo, s_hi)   (rank sub-slices)
+  unsigned na_bytes;  // levels whose per-head slab (H_l*W_l*C*4 bytes) exceeds this stream past L1 (no_allocate)
 };
 
 // Decode one sample: pixel coordinates -> clamped base pixel, corner mask, fractions.
@@ -96,6 +106,19 @@ __device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
   return d;
 }
 
+// Cache policy of the gather.  The fine pyramid levels have (almost) no reuse inside an SM -- a
+// 24x24-pixel window per anchor and two samples in it -- while one head's coarse levels (15x25: 48 KB,
+// 29x50: 186 KB) are re-read by every query: fine-level lines are loaded with L1::no_allocate so they
+// do not evict the coarse slabs (kHintBit of a sample's meta word selects the policy).
+constexpr int kHintBit = 1 << 30;
+__device__ __forceinline__ float4 ldg4_na(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg4_h(const float* p, bool na) { return na ? ldg4_na(p) : ldg4(p); }
+
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4_fma(float4& a, float s, const float4& v) {
   const u64 ss = pk(s, s);
@@ -131,15 +154,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ void epi_decode(const MsdaParams& p, long long item0, int s, float Wl, float Hl,
+__device__ __forceinline__ void epi_decode(const MsdaParams& p, size_t refrow, int s, float Wl, float Hl,
                                            const float* loc0, const float* att0, float2& xy, float& aw) {
   const float logit = __ldg(att0 + s);
   const float e = expf(logit - warp_max(logit));
   aw = __fdiv_rn(e, warp_sum(e));
   const float2 off = __ldg(reinterpret_cast<const float2*>(loc0) + s);
-  const unsigned bq = (unsigned)item0 / (unsigned)p.H;      // items < 2^31 on the vector path (vec_ok)
   const int z = (s % p.P) % p.D;
-  const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) + (size_t)bq * p.D + z);
+  const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) + refrow + z);   // refrow: anchor 0 of this row
   xy.x = __fadd_rn(__fdiv_rn(off.x, Wl), r.x);
   xy.y = __fadd_rn(__fdiv_rn(off.y, Hl), r.y);
 }
@@ -178,6 +200,45 @@ __device__ __forceinline__ size_t slab_offset(const MsdaParams& p, long long ite
   return (size_t)b * p.K * p.pix_stride + (size_t)h * p.C;
 }
 
+// Where a row's per-query data lives.  Plain: everything is indexed by the item (rebatched layout).
+// IDX: the row is (camera c, list entry j) -> pillar q; `dense` indexes per-(b, pillar, head) arrays
+// (BEV slots, and -- in the fused-prologue kernels -- the offsets / logits computed once per pillar).
+struct Row {
+  long long dense;   // ((b*Qd + q)*H + h)
+  size_t refrow;     // float2 index of the row's Z-anchor 0 in p.ref
+  float inv;         // output scale
+};
+template <bool IDX>
+__device__ __forceinline__ bool resolve_row(const MsdaParams& p, long long item0, Row& r) {
+  if (!IDX) {
+    r.dense = item0;
+    r.refrow = (size_t)((unsigned)item0 / (unsigned)p.H) * p.D;      // ref [B, Q, D, 2]
+    r.inv = 1.f;
+    return true;
+  }
+  const unsigned item = (unsigned)item0;
+  const unsigned h = item % (unsigned)p.H;
+  const unsigned nj = item / (unsigned)p.H;
+  const unsigned j = nj % (unsigned)p.Q, n = nj / (unsigned)p.Q;
+  const unsigned cl = n % (unsigned)p.ncl, b = n / (unsigned)p.ncl;
+  const unsigned c = (unsigned)p.cam0 + cl;
+  if (p.count && (int)j >= __ldg(p.count + c)) return false;
+  if (p.S > 1) {
+    const int sl = (int)((j >> 6) % (unsigned)p.S);
+    if (sl < p.s_lo || sl >= p.s_hi) return false;
+  }
+  const unsigned q = p.idx ? (unsigned)__ldg(p.idx + (size_t)c * p.Qd + j) : j;
+  const size_t bq = (size_t)b * p.Qd + q;
+  r.dense = (long long)(bq * p.H + h);
+  r.refrow = (((size_t)c * p.bs + b) * p.Qd + q) * p.D;             // reference_points_cam [cams, bs, Qd, D, 2]
+  r.inv = p.inv ? __ldg(p.inv + bq) : 1.f;
+  return true;
+}
+
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
 template <int CV>
 __device__ __forceinline__ void store_item(const MsdaParams& p, float* __restrict__ out,
                                            long long item, float4 acc, int g, int cl) {
@@ -194,8 +255,9 @@ __device__ __forceinline__ void store_item(const MsdaParams& p, float* __restric
 
 // MULTI = several items per warp (L*P a power of two < 32, one 32-sample chunk).
 // EPI = fused softmax / sampling-location epilogue (L*P == 32, !MULTI only).
-template <int CV, bool MULTI, bool EPI = false>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// 6 blocks (48 warps) per SM: the register cap (42) is what the tuned round-1 kernel used (40)
+template <int CV, bool MULTI, bool EPI = false, bool IDX = false>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 6)
 msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
   constexpr int NG = 32 / CV;       // sample groups per warp
   constexpr int ITERS = 32 / NG;    // == CV
@@ -204,11 +266,15 @@ msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
   const int cl = lane % CV;         // which float4 of the head vector
   long long item0;
   if (!warp_items(p, item0)) return;
+  Row row;
+  if (!resolve_row<IDX>(p, item0, row)) return;
 
   const int span = MULTI ? 32 : p.LP;                  // samples owned by this warp
   const int nchunks = MULTI ? 1 : (span + 31) >> 5;
-  const float* loc0 = p.loc + (size_t)item0 * p.LP * 2;
-  const float* att0 = p.attn + (size_t)item0 * p.LP;
+  // fused prologue + IDX: offsets / logits exist once per pillar (dense); otherwise per row
+  const long long prow = (EPI && IDX) ? row.dense : item0;
+  const float* loc0 = p.loc + (size_t)prow * p.LP * 2;
+  const float* att0 = p.attn + (size_t)prow * p.LP;
   const float* vb = p.value + slab_offset(p, item0) + cl * 4;   // moves with the item (MULTI)
   const unsigned pix = (unsigned)p.pix_stride;
 
@@ -226,13 +292,14 @@ msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
       float2 xy;
       float aw;
       if (EPI) {            // all 32 lanes are live here (L*P == 32)
-        epi_decode(p, item0, s, (float)Wl, (float)Hl, loc0, att0, xy, aw);
+        epi_decode(p, row.refrow, s, (float)Wl, (float)Hl, loc0, att0, xy, aw);
       } else {
         xy = __ldg(reinterpret_cast<const float2*>(loc0) + s);
         aw = __ldg(att0 + s);
       }
       float lh, lw;
       decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw, p.pix_stride);
+      if (meta && (unsigned)(Hl * Wl) * (unsigned)p.C * 4u > p.na_bytes) meta |= kHintBit;
       const float hh = 1.f - lh, hw = 1.f - lw;
       // invalid corners get weight 0; their (clamped) address aliases a valid corner's pixel
       w1 = (meta & 1) ? aw * (hh * hw) : 0.f;
@@ -263,12 +330,13 @@ msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
         // four independent 16-byte loads, issued back to back (32-bit offsets, 64-bit base)
         const unsigned o1 = (unsigned)sbase;                       // float offsets inside the slab
         const unsigned o2 = o1 + ((smeta & 16) ? pix : 0u);
-        const unsigned o3 = o1 + (unsigned)(smeta >> 5);
+        const unsigned o3 = o1 + (unsigned)((smeta & ~kHintBit) >> 5);
         const unsigned o4 = o3 + (o2 - o1);
-        const float4 v1 = ldg4(vbi + o1);
-        const float4 v2 = ldg4(vbi + o2);
-        const float4 v3 = ldg4(vbi + o3);
-        const float4 v4 = ldg4(vbi + o4);
+        const bool na = (smeta & kHintBit) != 0;      // warp-uniform when a level's points fill whole iterations
+        const float4 v1 = ldg4_h(vbi + o1, na);
+        const float4 v2 = ldg4_h(vbi + o2, na);
+        const float4 v3 = ldg4_h(vbi + o3, na);
+        const float4 v4 = ldg4_h(vbi + o4, na);
         f4_fma(acc, a1, v1);
         f4_fma(acc, a2, v2);
         f4_fma(acc, a3, v3);
@@ -276,11 +344,25 @@ msda_forward_kernel(const MsdaParams p, float* __restrict__ out) {
       }
     }
   }
+  if (IDX) {
+    // SpatialCrossAttention's scatter-add + count normalisation (spatial_cross_attention.py:164-171) as
+    // the epilogue: the head vector goes straight into the BEV slot of its pillar.
+#pragma unroll
+    for (int off = CV; off < 32; off <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+    }
+    if (g == 0) red_add_v4(out + (size_t)row.dense * p.C + cl * 4, f4_scale(row.inv, acc));
+    return;
+  }
   store_item<CV>(p, out, MULTI ? item0 + p.ipw - 1 : item0, acc, g, cl);
 }
 
-template <int CV, bool MULTI, bool EPI = false>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// 4 blocks (32 warps) per SM = 64 registers, the round-1 operating point
+template <int CV, bool MULTI, bool EPI = false, bool IDX = false>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
                      float* __restrict__ grad_value, float* __restrict__ grad_loc,
                      float* __restrict__ grad_attn) {
@@ -291,17 +373,22 @@ msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
   const int cl = lane % CV;
   long long item0;
   if (!warp_items(p, item0)) return;
+  Row row;
+  if (!resolve_row<IDX>(p, item0, row)) return;
 
   const int span = MULTI ? 32 : p.LP;
   const int nchunks = MULTI ? 1 : (span + 31) >> 5;
-  const float* loc0 = p.loc + (size_t)item0 * p.LP * 2;
-  const float* att0 = p.attn + (size_t)item0 * p.LP;
-  float* gloc0 = grad_loc + (size_t)item0 * p.LP * 2;
-  float* gatt0 = grad_attn + (size_t)item0 * p.LP;
+  const long long prow = (EPI && IDX) ? row.dense : item0;
+  const float* loc0 = p.loc + (size_t)prow * p.LP * 2;
+  const float* att0 = p.attn + (size_t)prow * p.LP;
+  float* gloc0 = grad_loc + (size_t)prow * p.LP * 2;
+  float* gatt0 = grad_attn + (size_t)prow * p.LP;
   const unsigned pix = (unsigned)p.pix_stride;
   size_t slab = slab_offset(p, item0) + cl * 4;
   float4 go = f4_zero();
-  if (!MULTI) go = ldg4(grad_out + (size_t)item0 * p.C + cl * 4);
+  // IDX: grad_out is the gradient of the BEV slot grid; the row's share is slot[pillar] / count
+  if (!MULTI) go = IDX ? f4_scale(row.inv, ldg4(grad_out + (size_t)row.dense * p.C + cl * 4))
+                       : ldg4(grad_out + (size_t)item0 * p.C + cl * 4);
 
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     const int s = chunk * 32 + lane;
@@ -315,12 +402,13 @@ msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
       const int Hl = (int)__ldg(p.shapes + 2 * l), Wl = (int)__ldg(p.shapes + 2 * l + 1);
       float2 xy;
       if (EPI) {
-        epi_decode(p, item0, s, (float)Wl, (float)Hl, loc0, att0, xy, aw);
+        epi_decode(p, row.refrow, s, (float)Wl, (float)Hl, loc0, att0, xy, aw);
       } else {
         xy = __ldg(reinterpret_cast<const float2*>(loc0) + s);
         aw = __ldg(att0 + s);
       }
       decode_sample(xy.x, xy.y, Hl, Wl, (int)__ldg(p.lsi + l), base, meta, lh, lw, p.pix_stride);
+      if (meta && (unsigned)(Hl * Wl) * (unsigned)p.C * 4u > p.na_bytes) meta |= kHintBit;
       fH = (float)Hl;
       fW = (float)Wl;
       const float hh = 1.f - lh, hw = 1.f - lw;
@@ -353,15 +441,16 @@ msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
       if (smeta & 15) {
         const unsigned o1 = (unsigned)sbase;                       // float offsets inside the slab
         const unsigned o2 = o1 + ((smeta & 16) ? pix : 0u);
-        const unsigned o3 = o1 + (unsigned)(smeta >> 5);
+        const unsigned o3 = o1 + (unsigned)((smeta & ~kHintBit) >> 5);
         const unsigned o4 = o3 + (o2 - o1);
         const float* vs = p.value + slab;
         float* gs = grad_value + slab;
         asm volatile("" : "+l"(vs), "+l"(gs));
-        const float4 v1 = ldg4(vs + o1);
-        const float4 v2 = ldg4(vs + o2);
-        const float4 v3 = ldg4(vs + o3);
-        const float4 v4 = ldg4(vs + o4);
+        const bool na = (smeta & kHintBit) != 0;
+        const float4 v1 = ldg4_h(vs + o1, na);
+        const float4 v2 = ldg4_h(vs + o2, na);
+        const float4 v3 = ldg4_h(vs + o3, na);
+        const float4 v4 = ldg4_h(vs + o4, na);
         // grad_value: top_grad * attn * corner weight as 16-byte vector reductions.  An
         // out-of-image corner has weight 0 and aliases a valid pixel: its reduction adds 0.
         red_add_v4(gs + o1, f4_scale(a1, go));
@@ -406,8 +495,14 @@ msda_backward_kernel(const MsdaParams p, const float* __restrict__ grad_out,
         // through loc = off / (W,H) + ref and w = softmax(logits): grad_off = grad_loc / (W,H),
         // grad_logit = w * (grad_w - sum_j w_j grad_w_j)   (all 32 lanes take part in the sum)
         const float dot = warp_sum(aw * ga);
-        gatt0[s] = aw * (ga - dot);
-        reinterpret_cast<float2*>(gloc0)[s] = make_float2(__fdiv_rn(gx, fW), __fdiv_rn(gy, fH));
+        if (IDX) {
+          // offsets / logits are shared by every camera that sees the pillar: accumulate (caller zeroes)
+          red_add_f32(gatt0 + s, aw * (ga - dot));
+          red_add_v2(gloc0 + 2 * s, __fdiv_rn(gx, fW), __fdiv_rn(gy, fH));
+        } else {
+          gatt0[s] = aw * (ga - dot);
+          reinterpret_cast<float2*>(gloc0)[s] = make_float2(__fdiv_rn(gx, fW), __fdiv_rn(gy, fH));
+        }
       } else {
         gatt0[s] = ga;
         reinterpret_cast<float2*>(gloc0)[s] = make_float2(gx, gy);
@@ -655,6 +750,21 @@ __global__ void msda_backward_generic_kernel(const MsdaParams p, const float* __
   }
 }
 
+// FORWARD only: per-head level slabs larger than this are read with L1::no_allocate (see ldg4_na).
+// Measured on B200, 6 cameras x 40000 queries (tools/exp_msda.py, profiles/r02_msda_cache_hints.json):
+//   off 2.44 ms | > 1 MB (level 0) 2.42 | > 256 KB (levels 0-1) 2.32 | > 100 KB (levels 0-2) 2.26
+// so everything but the 48 KB 15x25 level streams.  The backward gets slower with any of these
+// (4.60 -> 4.68 / 4.74 ms: its loads share the LSU -> XBAR request path with the reductions, and a
+// no-allocate miss cannot merge with a neighbouring warp's pending miss), so it keeps plain loads.
+// VIDAR_MSDA_STREAM_BYTES overrides the forward threshold (experiments; 0xffffffff = off).
+inline unsigned stream_threshold() {
+  static const unsigned v = [] {
+    const char* e = getenv("VIDAR_MSDA_STREAM_BYTES");
+    return e ? (unsigned)strtoul(e, nullptr, 0) : 100000u;
+  }();
+  return v;
+}
+
 int fill_params(MsdaParams& p, const float* value, const int64_t* shapes, const int64_t* lsi,
                 const float* loc, const float* attn, int B, int K, int H, int C, int L, int Q,
                 int P, int im2col_step, const char* who) {
@@ -679,13 +789,17 @@ int fill_params(MsdaParams& p, const float* value, const int64_t* shapes, const 
   p.pix_stride = H * C;
   p.ref = nullptr;
   p.D = 1;
+  p.idx = nullptr; p.count = nullptr; p.inv = nullptr;
+  p.ncl = B; p.cam0 = 0; p.bs = 1; p.Qd = Q;
+  p.S = 1; p.s_lo = 0; p.s_hi = 1;
+  p.na_bytes = stream_threshold();
   return VIDAR_OK;
 }
 
 inline int pick_ipw(int LP, int CV);
 // vector kernels: C in {16,32,64}, 32-bit intra-batch offsets and item counts
 inline bool vec_ok(const MsdaParams& p) {
-  return (p.C == 16 || p.C == 32 || p.C == 64) && (long long)p.K * p.H * p.C < (1LL << 26) &&   /* offsets ride in meta >> 5 */
+  return (p.C == 16 || p.C == 32 || p.C == 64) && (long long)p.K * p.H * p.C < (1LL << 25) &&   /* offsets ride in meta bits 5..29 */
          p.items < (1LL << 31) && (long long)p.Q * p.H < (1LL << 31);
 }
 inline void set_ipw(MsdaParams& p, int CV) {
@@ -761,6 +875,7 @@ extern "C" int vidar_msda_backward(const float* value, const int64_t* spatial_sh
   if (rc) return rc;
   VIDAR_REQUIRE(grad_out && grad_value && grad_sampling_loc && grad_attn_weight,
                 "ms_deform_attn_backward: null gradient pointer");
+  p.na_bytes = 0xffffffffu;
   cudaStream_t st = (cudaStream_t)stream;
   if (vec_ok(p)) {
     const int CV = C / 4;
@@ -839,6 +954,7 @@ extern "C" int vidar_msda_sca_backward(const float* value, const int64_t* spatia
   rc = check_sca(p, ref_points, D, who);
   if (rc) return rc;
   VIDAR_REQUIRE(grad_out && grad_value && grad_offsets && grad_logits, "%s: null gradient pointer", who);
+  p.na_bytes = 0xffffffffu;
   set_ipw(p, C / 4);
   const long long nb = num_blocks(p);
   VIDAR_REQUIRE(nb < 2147483647LL, "%s: problem too large", who);
@@ -849,3 +965,110 @@ extern "C" int vidar_msda_sca_backward(const float* value, const int64_t* spatia
   else msda_backward_kernel<16, false, true><<<grid, block, 0, st>>>(p, grad_out, grad_value, grad_offsets, grad_logits);
   return check_launch(who);
 }
+
+// ---- row-indirect entry points: SpatialCrossAttention's rebatch / scatter-add fused into the op ------
+// Rows are (camera, j) entries of per-camera visible-pillar lists (vidar_sca_compact); the forward adds
+// each row's head vectors, scaled by 1/#cameras, straight into the BEV slot grid and the backward reads
+// the slot gradient back through the same map (spatial_cross_attention.py:136-171 without the
+// [cams, max_len, C] intermediates, the index_add_ and the host sync on max_len).
+static int fill_rows(MsdaParams& p, const int32_t* idx, const int32_t* count, const float* inv, int bs, int ncl,
+                     int cam0, int Qd, int S, int s_lo, int s_hi, const char* who) {
+  VIDAR_REQUIRE(bs > 0 && ncl > 0 && cam0 >= 0 && Qd > 0, "%s: bad sizes bs=%d cameras=%d cam0=%d pillars=%d", who, bs, ncl, cam0, Qd);
+  VIDAR_REQUIRE(p.B == bs * ncl, "%s: value batch (%d) must be bs * cameras (%d x %d)", who, p.B, bs, ncl);
+  VIDAR_REQUIRE(p.Q <= Qd, "%s: rows per camera (%d) exceed the pillar count (%d)", who, p.Q, Qd);
+  VIDAR_REQUIRE(idx || p.Q == Qd, "%s: without an index list every pillar is a row (rows %d != pillars %d)", who, p.Q, Qd);
+  VIDAR_REQUIRE(S >= 1 && s_lo >= 0 && s_lo <= s_hi && s_hi <= S, "%s: bad sub-slice [%d, %d) of %d", who, s_lo, s_hi, S);
+  VIDAR_REQUIRE(vec_ok(p), "%s: head dim must be 16, 32 or 64 (got %d)", who, p.C);
+  p.idx = idx; p.count = count; p.inv = inv;
+  p.bs = bs; p.ncl = ncl; p.cam0 = cam0; p.Qd = Qd;
+  p.S = S; p.s_lo = s_lo; p.s_hi = s_hi;
+  p.ipw = 1;
+  p.lp_shift = 0;
+  return VIDAR_OK;
+}
+
+#define VIDAR_ROWS_LAUNCH(KERNEL, EPI_, ...)                                                     \
+  do {                                                                                           \
+    const long long nb = num_blocks(p);                                                          \
+    VIDAR_REQUIRE(nb < 2147483647LL, "%s: problem too large", who);                              \
+    const dim3 grid((unsigned)nb), block(kWarpsPerBlock * 32);                                   \
+    cudaStream_t st = (cudaStream_t)stream;                                                      \
+    if (p.C == 32) KERNEL<8, false, EPI_, true><<<grid, block, 0, st>>>(__VA_ARGS__);            \
+    else if (p.C == 16) KERNEL<4, false, EPI_, true><<<grid, block, 0, st>>>(__VA_ARGS__);       \
+    else KERNEL<16, false, EPI_, true><<<grid, block, 0, st>>>(__VA_ARGS__);                     \
+  } while (0)
+
+extern "C" int vidar_msda_rows_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                       const float* sampling_loc, const float* attn_weight, const int32_t* idx,
+                                       const int32_t* count, const float* inv_count, float* slots, int bs, int ncl,
+                                       int cam0, int K, int H, int C, int L, int Qrows, int Qd, int P, int S, int s_lo,
+                                       int s_hi, void* stream) {
+  const char* who = "msda_rows_forward";
+  MsdaParams p;
+  int rc = fill_params(p, value, spatial_shapes, level_start, sampling_loc, attn_weight, bs * ncl, K, H, C, L, Qrows, P,
+                       bs * ncl, who);
+  if (rc) return rc;
+  rc = fill_rows(p, idx, count, inv_count, bs, ncl, cam0, Qd, S, s_lo, s_hi, who);
+  if (rc) return rc;
+  VIDAR_REQUIRE(slots, "%s: null output", who);
+  VIDAR_ROWS_LAUNCH(msda_forward_kernel, false, p, slots);
+  return check_launch(who);
+}
+
+extern "C" int vidar_msda_rows_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                        const float* sampling_loc, const float* attn_weight, const int32_t* idx,
+                                        const int32_t* count, const float* inv_count, const float* grad_slots,
+                                        float* grad_value, float* grad_sampling_loc, float* grad_attn_weight, int bs,
+                                        int ncl, int cam0, int K, int H, int C, int L, int Qrows, int Qd, int P, int S,
+                                        int s_lo, int s_hi, void* stream) {
+  const char* who = "msda_rows_backward";
+  MsdaParams p;
+  int rc = fill_params(p, value, spatial_shapes, level_start, sampling_loc, attn_weight, bs * ncl, K, H, C, L, Qrows, P,
+                       bs * ncl, who);
+  if (rc) return rc;
+  rc = fill_rows(p, idx, count, inv_count, bs, ncl, cam0, Qd, S, s_lo, s_hi, who);
+  if (rc) return rc;
+  VIDAR_REQUIRE(grad_slots && grad_value && grad_sampling_loc && grad_attn_weight, "%s: null gradient pointer", who);
+  p.na_bytes = 0xffffffffu;
+  VIDAR_ROWS_LAUNCH(msda_backward_kernel, false, p, grad_slots, grad_value, grad_sampling_loc, grad_attn_weight);
+  return check_launch(who);
+}
+
+extern "C" int vidar_msda_sca_rows_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                           const float* ref_cam, const float* offsets, const float* logits,
+                                           const int32_t* idx, const int32_t* count, const float* inv_count, float* slots,
+                                           int bs, int ncl, int cam0, int K, int H, int C, int L, int Qrows, int Qd, int P,
+                                           int D, int S, int s_lo, int s_hi, void* stream) {
+  const char* who = "msda_sca_rows_forward";
+  MsdaParams p;
+  int rc = fill_params(p, value, spatial_shapes, level_start, offsets, logits, bs * ncl, K, H, C, L, Qrows, P, bs * ncl, who);
+  if (rc) return rc;
+  rc = check_sca(p, ref_cam, D, who);
+  if (rc) return rc;
+  rc = fill_rows(p, idx, count, inv_count, bs, ncl, cam0, Qd, S, s_lo, s_hi, who);
+  if (rc) return rc;
+  VIDAR_REQUIRE(slots, "%s: null output", who);
+  VIDAR_ROWS_LAUNCH(msda_forward_kernel, true, p, slots);
+  return check_launch(who);
+}
+
+extern "C" int vidar_msda_sca_rows_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                            const float* ref_cam, const float* offsets, const float* logits,
+                                            const int32_t* idx, const int32_t* count, const float* inv_count,
+                                            const float* grad_slots, float* grad_value, float* grad_offsets,
+                                            float* grad_logits, int bs, int ncl, int cam0, int K, int H, int C, int L,
+                                            int Qrows, int Qd, int P, int D, int S, int s_lo, int s_hi, void* stream) {
+  const char* who = "msda_sca_rows_backward";
+  MsdaParams p;
+  int rc = fill_params(p, value, spatial_shapes, level_start, offsets, logits, bs * ncl, K, H, C, L, Qrows, P, bs * ncl, who);
+  if (rc) return rc;
+  rc = check_sca(p, ref_cam, D, who);
+  if (rc) return rc;
+  rc = fill_rows(p, idx, count, inv_count, bs, ncl, cam0, Qd, S, s_lo, s_hi, who);
+  if (rc) return rc;
+  VIDAR_REQUIRE(grad_slots && grad_value && grad_offsets && grad_logits, "%s: null gradient pointer", who);
+  p.na_bytes = 0xffffffffu;
+  VIDAR_ROWS_LAUNCH(msda_backward_kernel, true, p, grad_slots, grad_value, grad_offsets, grad_logits);
+  return check_launch(who);
+}
+#undef VIDAR_ROWS_LAUNCH

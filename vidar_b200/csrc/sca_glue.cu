@@ -48,6 +48,63 @@ point_sampling_kernel(PsDims P, const float* __restrict__ ref3d, const float* __
   mask[idx] = ok ? 1 : 0;
 }
 
+
+// ---- visible-pillar lists of SpatialCrossAttention (spatial_cross_attention.py:136-140), on the device.
+// The reference runs `nonzero()` per camera on the host-visible mask and pads to the longest list (a
+// host sync per layer).  Here: one block per camera writes the ascending list of visible pillars of
+// batch element 0 and its length; consumers launch over the upper bound Q and exit on j >= count.
+__global__ void __launch_bounds__(1024)
+sca_compact_kernel(const unsigned char* __restrict__ mask, int* __restrict__ idx, int* __restrict__ count,
+                   int bs, int Q, int D) {
+  const int cam = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  const unsigned char* m = mask + (size_t)cam * bs * Q * D;       // batch element 0 of this camera
+  for (int q0 = 0; q0 < Q; q0 += 1024) {
+    const int q = q0 + tid;
+    bool hit = false;
+    if (q < Q) {
+      for (int d = 0; d < D; ++d) hit = hit || (m[(size_t)q * D + d] != 0);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    const int before = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int woff = 0, total = 0;
+    // 32 warp totals: every thread sums the prefix it needs (cheap, no second barrier for a scan)
+    for (int w = 0; w < 32; ++w) {
+      const int t = warp_tot[w];
+      if (w < warp) woff += t;
+      total += t;
+    }
+    const int base = base_s;
+    if (hit) idx[(size_t)cam * Q + base + woff + before] = q;
+    __syncthreads();
+    if (tid == 0) base_s = base + total;
+    __syncthreads();
+  }
+  if (tid == 0) count[cam] = base_s;
+}
+
+// 1 / clamp(#cameras whose mask hits pillar (b, q), 1)   (spatial_cross_attention.py:168-171)
+__global__ void __launch_bounds__(256)
+sca_inv_count_kernel(const unsigned char* __restrict__ mask, float* __restrict__ inv, int cams, int bs, int Q, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;            // over bs * Q
+  if (i >= bs * Q) return;
+  const int b = i / Q, q = i % Q;
+  int n = 0;
+  for (int c = 0; c < cams; ++c) {
+    const unsigned char* m = mask + (((size_t)c * bs + b) * Q + q) * D;
+    bool hit = false;
+    for (int d = 0; d < D; ++d) hit = hit || (m[d] != 0);
+    n += hit ? 1 : 0;
+  }
+  inv[i] = __fdiv_rn(1.f, (float)max(n, 1));
+}
+
 }  // namespace
 }  // namespace vidar
 
@@ -70,4 +127,16 @@ extern "C" int vidar_point_sampling(const float* ref3d, const float* lidar2img, 
   VIDAR_REQUIRE(nb < 2147483647LL, "point_sampling: problem too large");
   point_sampling_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(P, ref3d, lidar2img, ref_cam, bev_mask);
   return check_launch("point_sampling");
+}
+
+extern "C" int vidar_sca_compact(const unsigned char* bev_mask, int32_t* idx, int32_t* count, float* inv_count,
+                                 int cams, int bs, int Q, int D, void* stream) {
+  VIDAR_REQUIRE(bev_mask && idx && count && inv_count, "sca_compact: null pointer argument");
+  VIDAR_REQUIRE(cams > 0 && bs > 0 && Q > 0 && D > 0, "sca_compact: bad sizes cams=%d bs=%d Q=%d D=%d", cams, bs, Q, D);
+  cudaStream_t st = (cudaStream_t)stream;
+  sca_compact_kernel<<<(unsigned)cams, 1024, 0, st>>>(bev_mask, idx, count, bs, Q, D);
+  int rc = check_launch("sca_compact");
+  if (rc) return rc;
+  sca_inv_count_kernel<<<(unsigned)(((long long)bs * Q + 255) / 256), 256, 0, st>>>(bev_mask, inv_count, cams, bs, Q, D);
+  return check_launch("sca_compact(inv_count)");
 }

@@ -129,27 +129,18 @@ class MSDeformableAttention3D(BaseModule):
         return output
 
 
-_VISIBLE_CACHE = []      # [(weakref(bev_mask), version, (idx, live, max_len))], newest first
-
-
 def _visible_lists(bev_mask):
     """Per-camera lists of visible pillars (batch element 0, spatial_cross_attention.py:136-140) as
     (idx [cams, max_len] ascending pillar indices padded with invisible ones, live [cams, max_len]
-    bool, max_len).  One batched stable sort instead of six `nonzero()` calls and ONE host sync
-    (max_len); the encoder hands the same `bev_mask` tensor to all of its layers, so the lists are
-    cached on the tensor object (identity + in-place version): one sync per encoder call."""
-    import weakref
-    for ref, version, lists in _VISIBLE_CACHE:
-        if ref() is bev_mask and version == bev_mask._version:
-            return lists
+    bool, max_len) for the REBATCH path below (the reference's own data flow): one batched stable sort
+    instead of six `nonzero()` calls, and -- like the reference -- one host sync for max_len.  The
+    default (fused) path of SpatialCrossAttention needs neither the padding nor the sync."""
     hit = bev_mask[:, 0].sum(-1) > 0                                     # [cams, Q]
     counts = hit.sum(-1)
     max_len = int(counts.max())
     order = torch.argsort((~hit).to(torch.uint8), dim=1, stable=True)    # visible first, ascending
     idx = order[:, :max_len].contiguous()
     live = torch.arange(max_len, device=bev_mask.device)[None, :] < counts[:, None]
-    _VISIBLE_CACHE.insert(0, (weakref.ref(bev_mask), bev_mask._version, (idx, live, max_len)))
-    del _VISIBLE_CACHE[2:]
     return idx, live, max_len
 
 
@@ -157,7 +148,16 @@ def _visible_lists(bev_mask):
 class SpatialCrossAttention(BaseModule):
     """BEV query -> 6 camera feature pyramids (spatial_cross_attention.py:30-174): each camera
     attends only with the BEV pillars it sees, results are averaged over the cameras that
-    see a pillar, projected, and added to the residual."""
+    see a pillar, projected, and added to the residual.
+
+    Default data flow (`fuse_rebatch`): device-side visible lists, the sampling
+    offsets / attention logits computed once per pillar, and ONE kernel per direction that samples
+    every (camera, visible pillar) row and reduces it straight into the BEV slots
+    (vidar_b200/sca.py) -- no host sync, no [cams, max_len, C] buffers, no index_add_.
+    `process_group` (see `set_process_group`): the cameras are sharded over its ranks (SURVEY.md
+    8e); each rank projects and samples only its cameras, the partial slot grids are
+    reduce-scattered into row blocks, `output_proj` runs on the rank's rows and ONE all-gather
+    returns the replicated BEV grid."""
 
     def __init__(self, embed_dims=256, num_cams=6, pc_range=None, dropout=0.1, init_cfg=None,
                  batch_first=False,
@@ -173,10 +173,46 @@ class SpatialCrossAttention(BaseModule):
         self.num_cams = num_cams
         self.output_proj = nn.Linear(embed_dims, embed_dims)
         self.batch_first = batch_first
+        self.fuse_rebatch = True       # False: the reference's rebatch / index_add_ data flow
+        self.process_group = None
         self.init_weight()
 
     def init_weight(self):
         xavier_init(self.output_proj, distribution="uniform", bias=0.)
+
+    def set_process_group(self, group):
+        """Shard the cameras over `group` (None: single GPU).  `value_proj` then sees only this rank's
+        cameras, `output_proj` only its rows and the offsets / logits Linears only the gradient of this
+        rank's cameras: their parameter gradients are per-rank partial sums, tagged for
+        `sharding.allreduce_partial_grads` (one bucketed all-reduce per step)."""
+        self.process_group = group
+        partial = group is not None
+        da = self.deformable_attention
+        for m in (self.output_proj, getattr(da, "value_proj", None), getattr(da, "sampling_offsets", None),
+                  getattr(da, "attention_weights", None)):
+            if m is not None:
+                for p_ in m.parameters():
+                    p_.vidar_partial_grad = partial
+        return self
+
+    def _world(self):
+        g = self.process_group
+        if g is None:
+            return 1, 0
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            return 1, 0
+        return dist.get_world_size(g), dist.get_rank(g)
+
+    def _fusable(self, query, value, reference_points_cam):
+        da = self.deformable_attention
+        if not (self.fuse_rebatch and isinstance(da, MSDeformableAttention3D) and da.batch_first):
+            return False
+        if not (query.is_cuda and query.dtype == torch.float32 and value.dtype == torch.float32
+                and not torch.is_autocast_enabled()):
+            return False
+        D = reference_points_cam.size(3)
+        return MSDeformAttn3DFusedFunction.supported(da.num_levels, da.num_points, da.embed_dims // da.num_heads, D)
 
     def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, reference_points_cam=None,
@@ -188,9 +224,52 @@ class SpatialCrossAttention(BaseModule):
         inp_residual = query if residual is None else residual
         if query_pos is not None:
             query = query + query_pos
+        if self._fusable(query, value, reference_points_cam):
+            slots = self._slots_fused(query, value, reference_points_cam, bev_mask, spatial_shapes, level_start_index)
+        else:
+            if self._world()[0] > 1:
+                raise RuntimeError("camera sharding needs the fused SpatialCrossAttention path "
+                                   "(MSDeformableAttention3D with num_levels * num_points == 32, fp32, CUDA)")
+            slots = self._slots_rebatch(query, key, value, reference_points_cam, bev_mask, spatial_shapes, level_start_index)
+        world, _ = self._world()
+        if world > 1:
+            from .. import sharding
+            bs, Q, C = slots.shape
+            rows = sharding.reduce_scatter_rows(slots.reshape(bs * Q, C), self.process_group)     # this rank's pillars
+            rows = self.dropout(self.output_proj(rows))
+            full = sharding.all_gather_rows(rows, bs * Q, self.process_group).view(bs, Q, C)       # the BEV grid
+            return full + inp_residual          # the residual stays replicated (its gradient is the full one)
+        return self.dropout(self.output_proj(slots)) + inp_residual
+
+    # ---- default: rows sampled and reduced into the slots by one kernel (no rebatch tensors)
+    def _slots_fused(self, query, value, reference_points_cam, bev_mask, spatial_shapes, level_start_index):
+        from .. import sca
+        da = self.deformable_attention
+        bs, Q, C = query.shape
+        cams, K = value.shape[0], value.shape[1]
+        H, L, P = da.num_heads, da.num_levels, da.num_points
+        idx, count, inv = sca.compact_visible(bev_mask)
+        world, rank = self._world()
+        if world > 1:
+            # every rank samples only its cameras: the gradient that reaches the (replicated) query through
+            # offsets / logits is a per-rank partial sum -> one all-reduce of the 41 MB BEV-query gradient
+            from .. import sharding
+            query = sharding.sum_grad(query, self.process_group)
+        # Linear(query) rows are the same for every camera that sees the pillar: once per pillar
+        offsets = da.sampling_offsets(query).view(bs, Q, H, L, P, 2)
+        logits = da.attention_weights(query).view(bs, Q, H, L * P)
+        plan = sca.unit_plan(world, rank, cams)
+        values = []
+        for cam0, ncl, _, _, _ in plan:
+            v = value[cam0:cam0 + ncl].permute(2, 0, 1, 3).reshape(bs * ncl, K, C)      # [bs*ncl, K, C], batch-major
+            values.append(da.value_proj(v).view(bs * ncl, K, H, C // H))
+        return sca.SCARowsFunction.apply(plan, bs, spatial_shapes, level_start_index, reference_points_cam,
+                                         offsets, logits, idx, count, inv, *values)
+
+    # ---- the reference's data flow (:135-172) on the CUDA op: any deformable_attention module
+    def _slots_rebatch(self, query, key, value, reference_points_cam, bev_mask, spatial_shapes, level_start_index):
         bs, num_query, C = query.shape
         cams, D = self.num_cams, reference_points_cam.size(3)
-
         # visible-pillar lists per camera, taken from batch element 0 like the reference (:136-140)
         idx, live, max_len = _visible_lists(bev_mask)
 
@@ -214,9 +293,7 @@ class SpatialCrossAttention(BaseModule):
         slots.index_add_(1, idx.reshape(-1), out.reshape(bs, cams * max_len, self.embed_dims))
 
         count = (bev_mask.sum(-1) > 0).permute(1, 2, 0).sum(-1)              # [bs, Q] cameras seeing it
-        slots = slots / torch.clamp(count, min=1.0)[..., None]
-        slots = self.output_proj(slots)
-        return self.dropout(slots) + inp_residual
+        return slots / torch.clamp(count, min=1.0)[..., None]
 
 
 @ATTENTION.register_module()

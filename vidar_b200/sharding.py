@@ -64,3 +64,146 @@ def gather_rows(local_rows, world, total_rows, group=None):
         lo, hi = shard_range(total_rows, r, world)
         parts.append(buf[r, : hi - lo])
     return torch.cat(parts, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# Replicated <-> row-sharded conversions with autograd (the BEV-grid exchange of SURVEY.md 8e).
+#
+# Convention: tensors outside a sharded region are REPLICATED (every rank holds the same value and runs
+# the same downstream computation, so every rank also holds the same gradient).  Inside a region each
+# rank holds either a partial sum of the full tensor (camera-sharded SpatialCrossAttention slots) or a
+# contiguous block of its rows.
+#   reduce_scatter_rows : partial sums [R, C] on every rank  ->  this rank's rows of the total
+#                         (backward: all-gather of the row gradients -- d total / d partial_r = I)
+#   all_gather_rows     : this rank's rows  ->  the full replicated tensor  (the ONE all-gather of the BEV
+#                         grid; backward: the local slice of the replicated gradient, no communication)
+# Parameters used on sharded data (value_proj on a rank's cameras, output_proj / FFN on a rank's rows)
+# end up with PARTIAL gradients; they are tagged with `mark_partial` and summed over the group once per
+# step by `allreduce_partial_grads` (one bucketed all-reduce, like DDP's).
+# ------------------------------------------------------------------------------------------------
+def _rows_padded(n, world):
+    return -(-n // world)
+
+
+class _ReduceScatterRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, partial, group):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        R = partial.shape[0]
+        per = _rows_padded(R, world)
+        x = partial.contiguous()
+        if per * world != R:
+            pad = x.new_zeros((per * world,) + tuple(x.shape[1:]))
+            pad[:R] = x
+            x = pad
+        lo = rank * per
+        if dist.get_backend(group) == "gloo":          # CPU tests: gloo has no reduce_scatter
+            x = x.clone()
+            dist.all_reduce(x, group=group)
+            out = x[lo: lo + per]
+        else:
+            out = x.new_empty((per,) + tuple(x.shape[1:]))
+            dist.reduce_scatter_tensor(out, x, group=group)
+        n = max(0, min(R, lo + per) - lo)
+        ctx.meta = (group, R, per, world)
+        return out[:n]
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        group, R, per, world = ctx.meta
+        g = grad_rows.contiguous()
+        if g.shape[0] != per:
+            pad = g.new_zeros((per,) + tuple(g.shape[1:]))
+            pad[: g.shape[0]] = g
+            g = pad
+        full = g.new_empty((per * world,) + tuple(g.shape[1:]))
+        dist.all_gather_into_tensor(full, g, group=group)
+        return full[:R], None
+
+
+class _AllGatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, R, group):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        per = _rows_padded(R, world)
+        x = rows.contiguous()
+        if x.shape[0] != per:
+            pad = x.new_zeros((per,) + tuple(x.shape[1:]))
+            pad[: x.shape[0]] = x
+            x = pad
+        full = x.new_empty((per * world,) + tuple(x.shape[1:]))
+        dist.all_gather_into_tensor(full, x, group=group)
+        lo = rank * per
+        ctx.meta = (lo, max(0, min(R, lo + per) - lo))
+        return full[:R]
+
+    @staticmethod
+    def backward(ctx, grad_full):
+        lo, n = ctx.meta
+        return grad_full[lo: lo + n], None, None
+
+
+def row_range(R, rank, world):
+    """[lo, hi) of the rows `reduce_scatter_rows` / `all_gather_rows` give to `rank` (equal blocks of
+    ceil(R / world) rows, the last ones possibly short or empty)."""
+    per = _rows_padded(R, world)
+    lo = min(R, rank * per)
+    return lo, min(R, lo + per)
+
+
+def reduce_scatter_rows(partial, group):
+    """[R, ...] partial sums on every rank -> this rank's block of rows of the sum."""
+    return _ReduceScatterRows.apply(partial, group)
+
+
+def all_gather_rows(rows, R, group):
+    """This rank's block of rows -> the full [R, ...] tensor on every rank."""
+    return _AllGatherRows.apply(rows, R, group)
+
+
+def local_rows(full, group):
+    """The block of a replicated [R, ...] tensor that belongs to this rank (no communication)."""
+    lo, hi = row_range(full.shape[0], dist.get_rank(group), dist.get_world_size(group))
+    return full[lo:hi]
+
+
+def mark_partial(module):
+    """Tag a module's parameters: inside a sharded region their gradients are per-rank partial sums."""
+    for p in module.parameters():
+        p.vidar_partial_grad = True
+    return module
+
+
+def allreduce_partial_grads(module, group):
+    """Sum the gradients of every tagged parameter over `group` in ONE all-reduce."""
+    ps = [p for p in module.parameters() if getattr(p, "vidar_partial_grad", False) and p.grad is not None]
+    if not ps or dist.get_world_size(group) == 1:
+        return 0
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for p in ps:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off: off + n].view_as(p.grad))
+        off += n
+    return flat.numel()
+
+
+class _SumGrad(torch.autograd.Function):
+    """Identity whose backward sums the gradient over the group: for a REPLICATED tensor that every rank
+    consumes in a sharded computation (each rank's gradient is then a partial sum)."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, group=ctx.group)
+        return g, None
+
+
+def sum_grad(x, group):
+    return _SumGrad.apply(x, group)
