@@ -673,6 +673,105 @@ def run_reference(args):
     _emit(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: the synthetic ViDAR-RN101 pre-training step (vidar_b200/pretrain.py)
+# ------------------------------------------------------------------------------------------
+PRETRAIN_WORKLOAD = ("configs[3]: ViDAR-RN101 pre-training step, 1 sample: 4 frames (3 history no-grad + current) x 6 cams x "
+                     "3x928x1600 -> RN101+FPN(4 lvls, 256ch) -> 6-layer BEV encoder (TSA, SCA, LatentRendering@layer2, FFN; "
+                     "200x200 BEV) -> 3 future frames x 3-layer decoder -> 5 head frames x ray CE + dense Chamfer losses on "
+                     "40000 LiDAR-like rays; backward, gradient sync, clip, AdamW")
+
+
+def _eager_reference_ops():
+    """`--workload pretrain --impl reference`: MSDA and the LatentRendering core through the reference's torch formulas on the GPU
+    (mmcv's multi_scale_deformable_attn_pytorch / latent_rendering.py statements, as restated in oracle/),
+    the rest of the graph unchanged -- the same-box eager baseline of the two hot paths inside the step."""
+    from oracle import latent_render_ref, msda_ref
+    from vidar_b200.modules import deform_attn, latent_rendering
+
+    def msda_eager(value, shapes, lsi, loc, attn, im2col_step):
+        return msda_ref.msda_grid_sample(value, shapes, loc, attn)
+    deform_attn.msda_apply = msda_eager
+    act = {0: "exp", 1: "sigmoid"}
+
+    def core_eager(occ, feat, grid_num, grid_step, eps, act_id, group=None):
+        return latent_render_ref.latent_core(occ, feat, grid_num, grid_step, eps, act[act_id])
+    latent_rendering.latent_render_core = core_eager
+
+
+def run_pretrain(args):
+    import torch.distributed as dist
+
+    from vidar_b200 import _lib, pretrain
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    grp = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        grp = dist.group.WORLD
+    model, opt = pretrain.build(dev, grp)
+    eager = args.impl == "reference"
+    if eager:
+        _eager_reference_ops()
+        for layer in model.encoder:
+            layer.cross_attn.fuse_rebatch = False
+            layer.cross_attn.deformable_attention.fuse_epilogue = False
+            if layer.latent_render is not None:
+                layer.latent_render.fuse_projections = False
+    sample = pretrain.synthetic_sample(dev)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        loss, _ = pretrain.train_step(model, opt, sample, grp)
+    sync()
+    sampler.mark_begin()
+    n0 = _lib.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        loss, _ = pretrain.train_step(model, opt, sample, grp)
+    t1.record()
+    sync()
+    sampler.mark_end()
+    launches = _lib.launch_count() - n0
+    ms = t0.elapsed_time(t1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    _, stages = pretrain.train_step(model, opt, sample, grp, record=True)       # one more step with per-stage events
+    clocks = sampler.stop() if rank == 0 else None
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    if rank == 0:
+        agg = {}
+        for name, v in stages:
+            key = name.split(".")[-1] if name.startswith("hist") else name
+            key = ("history." + key) if name.startswith("hist") else key
+            agg[key] = agg.get(key, 0.0) + float(v)
+        _emit(json.dumps({
+            "metric": "ms/step (synthetic ViDAR-RN101 pre-training step: forward + backward + grad sync + AdamW)",
+            "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (cuDNN convolutions may use TF32, as in the reference's default PyTorch settings)",
+            "data": "synthetic (N(0,1) frames, nuScenes-like 6-camera rig, LiDAR-like rays)", "samples_per_s": 1e3 / ms,
+            "config": {"workload": PRETRAIN_WORKLOAD, "ops": "eager reference formulas (MSDA, LatentRendering core)" if eager else "vidar_b200 CUDA ops",
+                       "sharding": "one sample over all ranks: cameras (backbone, SCA) and BEV rows (SCA output, LatentRendering) sharded, rest replicated" if world > 1 else "single GPU"},
+            "impl": "reference (eager torch formulas of the two hot paths, same GPU)" if eager else "ours",
+            "stage_ms": agg, "loss": float(loss), "peak_mem_gb": peak_gb, "clocks": clocks, "gpu_launches": int(launches)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def _emit(line):
     """The JSON line is the ONLY thing this process writes to the real stdout."""
     os.write(_REAL_STDOUT, (line + "\n").encode())
@@ -692,9 +791,14 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hotpath", choices=["hotpath", "pretrain"],
+                    help="hotpath: BASELINE configs[1]+[2] (the headline line); pretrain: configs[3], the synthetic ViDAR-RN101 step "
+                         "(--impl reference there = the same graph with the reference's eager torch formulas for MSDA / LatentRendering, on the GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "pretrain":
+        run_pretrain(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -27,7 +27,8 @@ def timeit(fn, n=5, warm=2):
     return a.elapsed_time(b) / n
 
 
-res = {"stream_bytes": os.environ.get("VIDAR_MSDA_STREAM_BYTES", "default")}
+res = {"stream_bytes": os.environ.get("VIDAR_MSDA_STREAM_BYTES", "default"), "slab": os.environ.get("VIDAR_MSDA_SLAB", "default"),
+       "slab_fwd": os.environ.get("VIDAR_MSDA_SLAB_FWD", "0")}
 for tag, rows in (("dense", None), ("rebatched", 10240)):
     d = synthetic.sca_like_inputs(dev, rows=rows)
     cams = d["value"].shape[0]

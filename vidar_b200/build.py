@@ -81,11 +81,13 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static",
+    tmp = LIB + ".tmp"       # link next to the target, then rename: the library on disk is never half-written
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-cudart", "static",
            "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB)
     with open(STAMP, "w") as fh:
         fh.write(_digest())
     return LIB

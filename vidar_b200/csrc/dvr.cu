@@ -32,6 +32,7 @@
 // Launch: 64-thread blocks (30k rays -> 469 blocks over 148 SMs; the reference's
 // 1024-thread blocks give 30 blocks), one ray per thread, neighbouring rays in a warp.
 #include <float.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(kWarpRaysPerBlock * 32)
 render_warp_kernel(Grid G, const float* __restrict__ sigma, const float* __restrict__ origin,
                    const float* __restrict__ points, const float* __restrict__ tindex,
                    float* __restrict__ pred_dist, float* __restrict__ gt_dist,
-                   float* __restrict__ grad_sigma, int mode, int cap) {
+                   float* __restrict__ grad_sigma, int mode, int cap, double kTieEps) {
   using TR = Traits<V>;
   extern __shared__ double smem_d[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -497,7 +498,6 @@ render_warp_kernel(Grid G, const float* __restrict__ sigma, const float* __restr
   // decision hangs on the last bits: two axes crossing at (almost) the same parameter, or -- rounded-path
   // variants -- a path coordinate (almost) exactly on a .5 round() tie (e.g. half-integer origins: every
   // crossing).  Such rays are walked by the bit-faithful serial code instead.
-  constexpr double kTieEps = 1e-9;
   bool tie = false;
   {
     int v[3], gi[3];
@@ -745,6 +745,16 @@ bool warp_ray_config(const Grid& G, K kernel, int& cap, size_t& smem) {
   return true;
 }
 
+// relative distance below which two crossing times / a path coordinate and a .5 tie count as a near-tie
+// (render_warp_kernel); VIDAR_DVR_TIE_EPS overrides for experiments
+inline double tie_eps() {
+  static const double v = [] {
+    const char* e = getenv("VIDAR_DVR_TIE_EPS");
+    return e ? atof(e) : 1e-9;
+  }();
+  return v;
+}
+
 inline dim3 ray_grid(const Grid& G, int per_block) {
   return dim3((unsigned)((G.M + per_block - 1) / per_block), (unsigned)G.N);
 }
@@ -782,7 +792,7 @@ extern "C" int vidar_dvr_render_forward(const float* sigma, const float* origin,
   if (warp_ray_config(G, render_warp_kernel<V_DVR_FWD, false>, cap, smem)) {
     render_warp_kernel<V_DVR_FWD, false><<<ray_grid(G, kWarpRaysPerBlock), kWarpRaysPerBlock * 32, smem,
                                            (cudaStream_t)stream>>>(G, sigma, origin, points, tindex, pred_dist,
-                                                                   gt_dist, nullptr, train_phase, cap);
+                                                                   gt_dist, nullptr, train_phase, cap, tie_eps());
   } else {
     forward_kernel<V_DVR_FWD><<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
         G, sigma, origin, points, tindex, pred_dist, gt_dist, train_phase);
@@ -806,7 +816,7 @@ extern "C" int vidar_dvr_render(const float* sigma, const float* origin, const f
   if (warp_ray_config(G, render_warp_kernel<V_DVR_RENDER, true>, cap, smem)) {
     render_warp_kernel<V_DVR_RENDER, true><<<ray_grid(G, kWarpRaysPerBlock), kWarpRaysPerBlock * 32, smem,
                                              (cudaStream_t)stream>>>(G, sigma, origin, points, tindex, pred_dist,
-                                                                     gt_dist, grad_sigma, loss_type, cap);
+                                                                     gt_dist, grad_sigma, loss_type, cap, tie_eps());
   } else {
     render_grad_kernel<<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
         G, sigma, origin, points, tindex, pred_dist, gt_dist, grad_sigma, loss_type);

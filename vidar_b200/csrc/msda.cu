@@ -22,6 +22,7 @@
 // neighbouring blocks are the other heads of the same queries, so the lines a block
 // touches are neighbours in the image (L1/L2 locality).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -679,6 +680,8 @@ msda_backward_small_kernel(const MsdaParams p, const float* __restrict__ grad_ou
   }
 }
 
+#include "msda_slab.cuh"
+
 // ---- generic fallback (any C): one thread per (item, channel); scalar atomics.
 __global__ void msda_forward_generic_kernel(const MsdaParams p, float* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -825,6 +828,111 @@ inline long long num_blocks(const MsdaParams& p) {
   return (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
 }
 
+
+// ---- slab (persistent, shared-memory) variants: host side --------------------------------------
+// VIDAR_MSDA_SLAB: 0 = never, 1 = slab kernels with plain staging / flush, 2 = with TMA (default when the
+// driver exposes cuTensorMapEncodeTiled).
+inline int slab_mode() {
+  static const int v = [] {
+    const char* e = getenv("VIDAR_MSDA_SLAB");
+    return e ? atoi(e) : 2;
+  }();
+  return v;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled() {
+  static const EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// 2-D map over a [rows = B*K, cols = H*C] fp32 matrix (value or grad_value) with a [kSlabBoxRows x 32] box:
+// a head's 128-byte column slice of 128 consecutive pixel rows.
+inline bool make_slab_map(CUtensorMap* m, const float* base, long long rows, int cols) {
+  memset(m, 0, sizeof(*m));
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc || ((uintptr_t)base & 15u) || (cols & 3)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)kSlabBoxRows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline bool slab_ok(const MsdaParams& p) {
+  return slab_mode() > 0 && p.C == 32 && p.LP == 32 && p.P % 4 == 0 && p.L >= 1 && (p.pix_stride & (p.pix_stride - 1)) == 0 &&
+         vec_ok(p) && (long long)p.B * p.H < (1 << 20);
+}
+
+inline void slab_geo(const MsdaParams& p, SlabGeo& sg, int& grid) {
+  const int slots = 2 * kNumSMs;
+  const int nh = p.B * p.H;
+  sg.first_it = (p.LP - p.P) / 4;
+  sg.pix_shift = 0;
+  while ((1 << sg.pix_shift) < p.pix_stride) ++sg.pix_shift;
+  sg.tiles = (p.Q + kSlabWarps - 1) / kSlabWarps;
+  sg.parts = slots / nh > 1 ? slots / nh : 1;
+  if (sg.parts > sg.tiles) sg.parts = sg.tiles > 0 ? sg.tiles : 1;
+  sg.use_tma = 0;
+  const long long units = (long long)nh * sg.parts;
+  grid = (int)(units < slots ? units : slots);
+}
+
+constexpr size_t kSlabBwdSmem = (size_t)kSlabMaxRows * 128 + 2 * kSlabRecords * 4 + 2 * kSlabRecords * 4 + 2 * kSlabRecords * 2;
+constexpr size_t kSlabFwdSmem = (size_t)kSlabMaxRows * 128;
+
+template <bool EPI, bool IDX>
+int launch_slab_backward(MsdaParams& p, const float* grad_out, float* grad_value, float* grad_loc, float* grad_attn,
+                         cudaStream_t st, const char* who) {
+  SlabGeo sg;
+  int grid;
+  slab_geo(p, sg, grid);
+  CUtensorMap map;
+  sg.use_tma = (slab_mode() >= 2 && make_slab_map(&map, grad_value, (long long)p.B * p.K, p.pix_stride)) ? 1 : 0;
+  if (!sg.use_tma) memset(&map, 0, sizeof(map));
+  auto k = msda_backward_slab_kernel<EPI, IDX>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlabBwdSmem) != cudaSuccess)
+    return set_error(VIDAR_E_CUDA, "%s: cannot opt in to %zu bytes of shared memory", who, kSlabBwdSmem);
+  k<<<grid, kSlabWarps * 32, kSlabBwdSmem, st>>>(p, sg, map, grad_out, grad_value, grad_loc, grad_attn);
+  return check_launch(who);
+}
+
+template <bool EPI, bool IDX>
+int launch_slab_forward(MsdaParams& p, float* out, cudaStream_t st, const char* who) {
+  SlabGeo sg;
+  int grid;
+  slab_geo(p, sg, grid);
+  CUtensorMap map;
+  sg.use_tma = (slab_mode() >= 2 && make_slab_map(&map, p.value, (long long)p.B * p.K, p.pix_stride)) ? 1 : 0;
+  if (!sg.use_tma) memset(&map, 0, sizeof(map));
+  auto k = msda_forward_slab_kernel<EPI, IDX>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlabFwdSmem) != cudaSuccess)
+    return set_error(VIDAR_E_CUDA, "%s: cannot opt in to %zu bytes of shared memory", who, kSlabFwdSmem);
+  k<<<grid, kSlabWarps * 32, kSlabFwdSmem, st>>>(p, sg, map, out);
+  return check_launch(who);
+}
+
+// VIDAR_MSDA_SLAB_FWD=1: the forward also runs its slab variant (off by default)
+inline bool slab_forward_on() {
+  static const bool v = [] {
+    const char* e = getenv("VIDAR_MSDA_SLAB_FWD");
+    return e && atoi(e) != 0;
+  }();
+  return v;
+}
+
 }  // namespace
 }  // namespace vidar
 
@@ -840,6 +948,7 @@ extern "C" int vidar_msda_forward(const float* value, const int64_t* spatial_sha
   if (rc) return rc;
   VIDAR_REQUIRE(out, "ms_deform_attn_forward: null output");
   cudaStream_t st = (cudaStream_t)stream;
+  if (slab_ok(p) && slab_forward_on()) return launch_slab_forward<false, false>(p, out, st, "ms_deform_attn_forward");
   if (vec_ok(p)) {
     const int CV = C / 4;
     set_ipw(p, CV);
@@ -877,6 +986,9 @@ extern "C" int vidar_msda_backward(const float* value, const int64_t* spatial_sh
                 "ms_deform_attn_backward: null gradient pointer");
   p.na_bytes = 0xffffffffu;
   cudaStream_t st = (cudaStream_t)stream;
+  if (slab_ok(p))
+    return launch_slab_backward<false, false>(p, grad_out, grad_value, grad_sampling_loc, grad_attn_weight, st,
+                                              "ms_deform_attn_backward");
   if (vec_ok(p)) {
     const int CV = C / 4;
     set_ipw(p, CV);
@@ -931,6 +1043,7 @@ extern "C" int vidar_msda_sca_forward(const float* value, const int64_t* spatial
   rc = check_sca(p, ref_points, D, who);
   if (rc) return rc;
   VIDAR_REQUIRE(out, "%s: null output", who);
+  if (slab_ok(p) && slab_forward_on()) return launch_slab_forward<true, false>(p, out, (cudaStream_t)stream, who);
   set_ipw(p, C / 4);
   const long long nb = num_blocks(p);
   VIDAR_REQUIRE(nb < 2147483647LL, "%s: problem too large", who);
@@ -955,6 +1068,7 @@ extern "C" int vidar_msda_sca_backward(const float* value, const int64_t* spatia
   if (rc) return rc;
   VIDAR_REQUIRE(grad_out && grad_value && grad_offsets && grad_logits, "%s: null gradient pointer", who);
   p.na_bytes = 0xffffffffu;
+  if (slab_ok(p)) return launch_slab_backward<true, false>(p, grad_out, grad_value, grad_offsets, grad_logits, (cudaStream_t)stream, who);
   set_ipw(p, C / 4);
   const long long nb = num_blocks(p);
   VIDAR_REQUIRE(nb < 2147483647LL, "%s: problem too large", who);
@@ -1011,6 +1125,7 @@ extern "C" int vidar_msda_rows_forward(const float* value, const int64_t* spatia
   rc = fill_rows(p, idx, count, inv_count, bs, ncl, cam0, Qd, S, s_lo, s_hi, who);
   if (rc) return rc;
   VIDAR_REQUIRE(slots, "%s: null output", who);
+  if (slab_ok(p) && slab_forward_on()) return launch_slab_forward<false, true>(p, slots, (cudaStream_t)stream, who);
   VIDAR_ROWS_LAUNCH(msda_forward_kernel, false, p, slots);
   return check_launch(who);
 }
@@ -1030,6 +1145,8 @@ extern "C" int vidar_msda_rows_backward(const float* value, const int64_t* spati
   if (rc) return rc;
   VIDAR_REQUIRE(grad_slots && grad_value && grad_sampling_loc && grad_attn_weight, "%s: null gradient pointer", who);
   p.na_bytes = 0xffffffffu;
+  if (slab_ok(p))
+    return launch_slab_backward<false, true>(p, grad_slots, grad_value, grad_sampling_loc, grad_attn_weight, (cudaStream_t)stream, who);
   VIDAR_ROWS_LAUNCH(msda_backward_kernel, false, p, grad_slots, grad_value, grad_sampling_loc, grad_attn_weight);
   return check_launch(who);
 }
@@ -1048,6 +1165,7 @@ extern "C" int vidar_msda_sca_rows_forward(const float* value, const int64_t* sp
   rc = fill_rows(p, idx, count, inv_count, bs, ncl, cam0, Qd, S, s_lo, s_hi, who);
   if (rc) return rc;
   VIDAR_REQUIRE(slots, "%s: null output", who);
+  if (slab_ok(p) && slab_forward_on()) return launch_slab_forward<true, true>(p, slots, (cudaStream_t)stream, who);
   VIDAR_ROWS_LAUNCH(msda_forward_kernel, true, p, slots);
   return check_launch(who);
 }
@@ -1068,6 +1186,8 @@ extern "C" int vidar_msda_sca_rows_backward(const float* value, const int64_t* s
   if (rc) return rc;
   VIDAR_REQUIRE(grad_slots && grad_value && grad_offsets && grad_logits, "%s: null gradient pointer", who);
   p.na_bytes = 0xffffffffu;
+  if (slab_ok(p))
+    return launch_slab_backward<true, true>(p, grad_slots, grad_value, grad_offsets, grad_logits, (cudaStream_t)stream, who);
   VIDAR_ROWS_LAUNCH(msda_backward_kernel, true, p, grad_slots, grad_value, grad_offsets, grad_logits);
   return check_launch(who);
 }
