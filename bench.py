@@ -147,7 +147,7 @@ def bench_config(world):
                          "(vidar_b200.sca.unit_plan); per step: reduce-scatter of the partial BEV slot grids "
                          "(41 MB) + ONE all-gather of the BEV grid, backward = all-gather of the row gradients; "
                          "rays split over ranks, one all-reduce of both ray stages' grad_sigma (2 x 7.7 MB); "
-                         "LatentRendering: BEV rows/cells split over ranks") if world > 1 else "single GPU"}
+                         "LatentRendering: BEV rows/cells split over ranks, row-sharded in/out (all-gather of the 2.56 MB maps only)") if world > 1 else "single GPU"}
 
 
 def run_ours(args):
@@ -209,6 +209,7 @@ def run_ours(args):
     embed = torch.randn(1, GRID[1], GRID[2], EMBED, device=dev, generator=lg)
     grad_embed = torch.randn(1, GRID[1], GRID[2], EMBED, device=dev, generator=lg)
 
+    lr0, lr1 = sharding.shard_range(GRID[1] * GRID[2], rank, world)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     names = ["msda_fwd", "msda_bwd", "latent_render", "ray_ce", "render"]
     ray_grads = torch.empty((2,) + tuple(sigma.shape[1:]), device=dev) if world > 1 else None
@@ -245,9 +246,15 @@ def run_ours(args):
                     dist.all_reduce(t[0].grad[c - cam0], group=cam_groups[c])
         if record:
             e[2].record()
-        emb = embed.detach().requires_grad_(True)
         latent.zero_grad(set_to_none=True)
-        latent(emb).backward(grad_embed)
+        if world > 1:
+            # row-sharded in / out (the module's consumers in the encoder -- LayerNorm, FFN -- are row-wise): only the
+            # 2.56 MB occupancy / feature / prob maps cross NVLink, never the 41 MB grid
+            emb = embed.view(-1, EMBED)[lr0:lr1].detach().requires_grad_(True)
+            latent.forward_rows(emb, 1, GRID[1], GRID[2]).backward(grad_embed.view(-1, EMBED)[lr0:lr1])
+        else:
+            emb = embed.detach().requires_grad_(True)
+            latent(emb).backward(grad_embed)
         if record:
             e[3].record()
         sg = sigma[0].detach().requires_grad_(True)
@@ -280,12 +287,40 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(False)
     sync()
+    # ---- the step as ONE CUDA graph (kernels, memsets and the NCCL collectives): at N > 1 the ~40 launches
+    #      and ~10 collectives of a 2 ms step are otherwise bound by the host's launch rate, not by the GPUs
+    graph, mode = None, "eager"
+    if args.graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step(False)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            sync()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                last = step(False)
+            mode = "cuda graph replay (one graph per step)"
+            graph.replay()                       # first replay outside the timed region
+            sync()
+        except Exception as ex:                  # capture is an optimisation: fall back to eager launches
+            graph, mode = None, f"eager (graph capture failed: {type(ex).__name__}: {str(ex)[:120]})"
+            torch.cuda.synchronize()
+    ok = torch.tensor([1 if graph is not None else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0 and graph is not None:   # every rank must take the same path
+        graph, mode = None, "eager (graph capture failed on another rank)"
     sampler.mark_begin()
     n0 = _lib.launch_count()
     t0, t1 = ev(), ev()
     t0.record()
     for _ in range(args.steps):
-        last = step(True)
+        if graph is not None:
+            graph.replay()
+        else:
+            last = step(True)
     t1.record()
     sync()
     sampler.mark_end()
@@ -297,6 +332,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_step = total_ms / args.steps
+    if graph is not None:
+        # per-stage breakdown (and the roofline's kernel time): the same step launched eagerly with events between
+        # the stages -- identical kernels, outside the headline's timed region
+        n1 = _lib.launch_count()
+        for _ in range(args.steps):
+            last = step(True)
+        sync()
+        launches = _lib.launch_count() - n1     # launches of K steps (a replayed graph does not pass through the C entry points)
     parts = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, n in enumerate(names)}
 
     if os.environ.get("VIDAR_BENCH_PROFILE") == "1":   # under ncu: kernels only
@@ -455,7 +498,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (seeded: perspective pillar fan per camera, LiDAR-like rays)",
         "config": bench_config(world),
-        "breakdown_ms": parts, "sharded_check": sharded_check, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "breakdown_ms": parts, "launch_mode": mode, "sharded_check": sharded_check, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "msda_query_samples_per_s": NUM_CAMS * BEV_Q * HEADS * len(LEVELS) * POINTS / ((parts["msda_fwd"] + parts["msda_bwd"]) * 1e-3),
     }
@@ -514,7 +557,10 @@ def check_sharded(dev, rank, world, grp, last, groups, msda_stage, grad_bev, lat
     ro = latent(emb)
     ro.backward(grad_embed)
     latent.process_group = pg
-    out["latent_grad_embed"] = rel(gemb, emb.grad)
+    # the sharded step returns this rank's rows of grad_embed: compare them with the same rows of the full gradient
+    from vidar_b200 import sharding
+    a0, a1 = sharding.shard_range(GRID[1] * GRID[2], rank, world)
+    out["latent_grad_embed_rows"] = rel(gemb, emb.grad.view(-1, EMBED)[a0:a1])
     worst = torch.tensor([max(out.values())], device=dev)
     dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=grp)
     out["max_over_ranks"] = float(worst.item())
@@ -791,6 +837,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the timed steps eagerly instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="hotpath", choices=["hotpath", "pretrain"],
                     help="hotpath: BASELINE configs[1]+[2] (the headline line); pretrain: configs[3], the synthetic ViDAR-RN101 step "
                          "(--impl reference there = the same graph with the reference's eager torch formulas for MSDA / LatentRendering, on the GPU)")

@@ -62,3 +62,18 @@ def dvr_inputs_outside(seed=11, M=800, zero_length=True):
     if not zero_length:
         tindex[0, :5] = -1
     return sigma, origin, points, tindex
+
+
+def dvr_inputs_ties(seed=123, M=6000):
+    """Tie-prone rays: integer, HALF-INTEGER (every crossing is a round() tie of the rounded-path variants)
+    and generic origins; a share of the end points on the integer / half-integer lattice (crossing times of
+    two axes coincide).  Branch decisions on such rays hang on the last bits of the traversal arithmetic."""
+    rng = np.random.default_rng(seed)
+    Z, Y, X = 8, 50, 50
+    sigma = rng.uniform(0, 1, (1, 3, Z, Y, X)).astype(np.float32)
+    origin = np.array([[[25.0, 25.0, 4.0], [24.5, 25.5, 3.5], [24.37, 25.61, 3.52]]], np.float32)
+    points = (rng.uniform(0, 1, (1, M, 3)) * np.array([60, 60, 10]) - np.array([5, 5, 1])).astype(np.float32)
+    points[0, ::7] = np.round(points[0, ::7])
+    points[0, ::11] = np.round(points[0, ::11] * 2) / 2
+    tindex = rng.integers(0, 3, (1, M)).astype(np.float32)
+    return sigma, origin, points, tindex

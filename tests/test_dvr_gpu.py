@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import dvr_ref
-from tests.inputs import dvr_inputs_cfg1, dvr_inputs_lidar, dvr_inputs_outside
+from tests.inputs import dvr_inputs_cfg1, dvr_inputs_lidar, dvr_inputs_outside, dvr_inputs_ties
 from vidar_b200 import render
 
 pytestmark = pytest.mark.gpu
@@ -198,14 +198,8 @@ def test_warp_per_ray_voxel_mismatch_rate(cuda):
     serial reference's only on near-exact ties.  Randomised rays from integer, half-integer and generic
     origins -- the tie-prone cases -- against the C oracle: a different voxel shows up as a pred
     difference far above 1e-12; the count must be zero at the ray-caster tolerance."""
-    rng = np.random.default_rng(123)
-    Z, Y, X, M = 8, 50, 50, 6000
-    sigma = rng.uniform(0, 1, (1, 3, Z, Y, X)).astype(np.float32)
-    origin = np.array([[[25.0, 25.0, 4.0], [24.5, 25.5, 3.5], [24.37, 25.61, 3.52]]], np.float32)
-    points = (rng.uniform(0, 1, (1, M, 3)) * np.array([60, 60, 10]) - np.array([5, 5, 1])).astype(np.float32)
-    points[0, ::7] = np.round(points[0, ::7])               # axis-aligned-ish / lattice end points
-    points[0, ::11] = np.round(points[0, ::11] * 2) / 2
-    tindex = rng.integers(0, 3, (1, M)).astype(np.float32)
+    sigma, origin, points, tindex = dvr_inputs_ties()
+    Z, Y, X = sigma.shape[2:]
     s, o, p, t = _t(cuda, sigma, origin, points, tindex)
     bad = 0
     for phase in ("test", "train"):

@@ -63,6 +63,22 @@ def _module_worker(rank, world, port, out):
             o = m(e)
             o.backward(c["grad"].cuda())
             res.append([o.detach().cpu(), e.grad.cpu()] + [p.grad.cpu() for _, p in sorted(m.named_parameters())])
+        # row-sharded I/O: this rank's rows in, this rank's rows out (no 41 MB all-gather); gathered here for the check
+        from vidar_b200.sharding import shard_range
+        R = bs * bev[0] * bev[1]
+        lo, hi = shard_range(R, rank, world)
+        m.process_group = dist.group.WORLD
+        m.zero_grad(set_to_none=True)
+        e = c["embed"].cuda().view(R, -1)[lo:hi].clone().requires_grad_(True)
+        o = m.forward_rows(e, bs, bev[0], bev[1])
+        o.backward(c["grad"].cuda().view(R, -1)[lo:hi])
+        parts = []
+        for t in (o.detach(), e.grad):
+            buf = [torch.empty((shard_range(R, r, world)[1] - shard_range(R, r, world)[0], t.shape[1]), device="cuda")
+                   for r in range(world)]
+            dist.all_gather(buf, t.contiguous())
+            parts.append(torch.cat(buf, 0).view(c["embed"].shape).cpu())
+        res.append(parts + [p.grad.cpu() for _, p in sorted(m.named_parameters())])
     if rank == 0:
         torch.save(res, out)
     dist.barrier()
@@ -77,7 +93,8 @@ def test_sharded_fused_module_equals_single_gpu(tmp_path):
     out = str(tmp_path / "m.pt")
     mp.spawn(_module_worker, args=(2, 29440 + os.getpid() % 200, out), nprocs=2, join=True)
     res = torch.load(out, weights_only=False)
-    for single, sharded in ((res[0], res[1]), (res[2], res[3])):
+    # per case: [single, sharded (replicated in/out), sharded (row-sharded in/out)]
+    for single, sharded in ((res[0], res[1]), (res[0], res[2]), (res[3], res[4]), (res[3], res[5])):
         for i, (a, b) in enumerate(zip(sharded, single)):
             torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5 * float(b.abs().max()), msg=lambda m: f"tensor {i}: {m}")
 

@@ -19,13 +19,14 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import build_ref  # noqa: E402
-from tests.inputs import dvr_inputs_cfg1, dvr_inputs_lidar, dvr_inputs_outside  # noqa: E402
+from tests.inputs import dvr_inputs_cfg1, dvr_inputs_lidar, dvr_inputs_outside, dvr_inputs_ties  # noqa: E402
 
 CASES = {
     "cfg1_int": lambda: dvr_inputs_cfg1(seed=0, integer_origin=True),
     "cfg1_frac": lambda: dvr_inputs_cfg1(seed=0, integer_origin=False),
     "lidar_small": lambda: dvr_inputs_lidar(M=1500, T=2, grid=(8, 64, 64), seed=5, pad=12),
     "outside": lambda: dvr_inputs_outside(zero_length=False),
+    "ties": lambda: dvr_inputs_ties(M=3000),
 }
 
 

@@ -105,5 +105,44 @@ def main():
     print(open(os.path.join(DST, f"{TAG}_launches_summary.txt")).read()[:1800])
 
 
+def sass_evidence(lib="vidar_b200/libvidar_b200.so", out="profiles/r02_sass_evidence.txt"):
+    """`cuobjdump -sass` mnemonic counts per kernel -> profiles/ (what proves Blackwell-native code:
+    FFMA2, REDG...F32x4, UTMALDG / UTMAREDG, SYNCS).  python tools/summarize_profiles.py --sass"""
+    import collections
+    import re
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    cur, stats = None, collections.OrderedDict()
+    pat = re.compile(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Za-z0-9_.]+)")
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            stats[cur] = collections.Counter()
+            continue
+        m = pat.match(line)
+        if m and cur:
+            stats[cur][m.group(1)] += 1
+    keys = ["FFMA2", "RED", "LDG.E.NA", "LDG.E.128", "UTMALDG", "UTMAREDG", "SYNCS", "DFMA", "ATOMS", "SHFL", "BAR"]
+    names = subprocess.run(["c++filt"], input="\n".join(stats), capture_output=True, text=True).stdout.splitlines()
+    lines = ["SASS evidence for " + lib + " (sm_100a): `cuobjdump -sass` mnemonic counts per kernel (tools/summarize_profiles.py --sass).",
+             "FFMA2 = packed fp32 FMA (fma.rn.f32x2); RED = red.global.add (the .F32x4 form is the 16-byte vector reduction); LDG.E.NA = "
+             "ld.global.nc.L1::no_allocate; UTMALDG / UTMAREDG = cp.async.bulk.tensor / cp.reduce.async.bulk.tensor (TMA); SYNCS = mbarrier.", ""]
+    for (mangled, c), d in zip(stats.items(), names):
+        short = re.sub(r"\(.*", "", d.replace("vidar::(anonymous namespace)::", ""))
+        cells = []
+        for k in keys:
+            hits = {kk: v for kk, v in c.items() if kk.startswith(k)}
+            if hits:
+                cells.append(f"{k}:{sum(hits.values())}" + (f"({max(hits, key=hits.get)})" if k == "RED" else ""))
+        lines.append(f"{short:72s} instrs {sum(c.values()):6d}  " + "  ".join(cells))
+    with open(out, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return out
+
+
 if __name__ == "__main__":
-    main()
+    if "--sass" in sys.argv:
+        print(sass_evidence())
+    else:
+        main()

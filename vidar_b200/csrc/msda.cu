@@ -830,12 +830,15 @@ inline long long num_blocks(const MsdaParams& p) {
 
 
 // ---- slab (persistent, shared-memory) variants: host side --------------------------------------
-// VIDAR_MSDA_SLAB: 0 = never, 1 = slab kernels with plain staging / flush, 2 = with TMA (default when the
-// driver exposes cuTensorMapEncodeTiled).
+// VIDAR_MSDA_SLAB: 0 = off (default), 1 = slab kernels with plain staging / flush, 2 = with TMA.  Measured on
+// B200 (profiles/r02_msda_slab_experiment.json): backward 4.48 -> 5.25 ms, forward 2.06 -> 2.19 ms per 6
+// cameras -- the shared-memory hand-over costs more than the 25 % of reduction lines it removes (a barrier
+// per 16-query tile, ~10 issue slots per record, half the L1), with or without TMA.  The variants stay
+// selectable (and parity-tested, tests/test_msda_gpu.py::test_slab_variants) but off.
 inline int slab_mode() {
   static const int v = [] {
     const char* e = getenv("VIDAR_MSDA_SLAB");
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 0;
   }();
   return v;
 }

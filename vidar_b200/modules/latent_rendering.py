@@ -160,21 +160,34 @@ class _FusedLatentRendering(torch.autograd.Function):
     replicated, so the node is a drop-in for the single-GPU one."""
 
     @staticmethod
-    def forward(ctx, embed, w_occ, b_occ, w_feat, b_feat, w_b, b_b, grid_num, grid_step, eps, act, group):
+    def forward(ctx, embed, w_occ, b_occ, w_feat, b_feat, w_b, b_b, grid_num, grid_step, eps, act, group, rows_io=None):
+        """`rows_io` = (bs, Hb, Wb): `embed` holds only THIS RANK's rows [n, E] of the [bs*Hb*Wb, E] BEV grid and
+        only its rows of the output are returned (row-wise consumers -- LayerNorm, FFN -- need no more): the two
+        41 MB all-gathers of the replicated mode disappear."""
         import torch.distributed as dist
         from ..sharding import gather_rows, shard_range
         _lib.require_cuda(embed=embed.contiguous())
         params = [p.detach().float().contiguous() for p in (w_occ, b_occ, w_feat, b_feat, w_b, b_b)]
         w_occ, b_occ, w_feat, b_feat, w_b, b_b = params
-        bs, Hb, Wb, E = embed.shape
-        D, A = w_occ.shape[0], w_feat.shape[0]
-        R = bs * Hb * Wb
-        x = embed.detach().float().contiguous().view(R, E)
         world = _group_world(group)
+        D, A = w_occ.shape[0], w_feat.shape[0]
+        if rows_io is not None:
+            bs, Hb, Wb = rows_io
+            E = embed.shape[-1]
+        else:
+            bs, Hb, Wb, E = embed.shape
+        R = bs * Hb * Wb
         c0, c1 = shard_range(R, dist.get_rank(group), world) if world > 1 else (0, R)
         n = c1 - c0
+        if rows_io is not None:
+            if embed.numel() != n * E:
+                raise RuntimeError(f"rows_io: expected this rank's {n} rows of {E} channels, got {tuple(embed.shape)}")
+            x_l = embed.detach().float().contiguous().view(n, E)
+        else:
+            x_l = embed.detach().float().contiguous().view(R, E)[c0:c1]
         dev = embed.device
-        alloc = torch.zeros if world > 1 else torch.empty
+        even = world > 1 and R % world == 0           # equal contiguous shards: all-gather instead of zero-padded all-reduce
+        alloc = torch.zeros if (world > 1 and not even) else torch.empty
         flat = alloc(R * (D + A), dtype=torch.float32, device=dev)       # occ | feat in one buffer: one collective
         occ, feat = flat[: R * D].view(R, D), flat[R * D:].view(R, A)
         prob = alloc((R, D), dtype=torch.float32, device=dev)
@@ -184,33 +197,48 @@ class _FusedLatentRendering(torch.autograd.Function):
         L = _lib.lib()
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            _lib.check(L.vidar_latent_proj_in_forward(_lib.ptr(x[c0:c1]), _lib.ptr(w_occ), _lib.ptr(b_occ), _lib.ptr(w_feat),
-                                                      _lib.ptr(b_feat), _lib.ptr(occ[c0:c1]), _lib.ptr(feat[c0:c1]), n, E, D, A, st))
-            if world > 1:
-                dist.all_reduce(flat, group=group)
+            if even:
+                # this rank's [occ rows | feat rows] contiguous -> ONE all-gather, then two strided copies into the maps
+                mine = torch.empty(n * (D + A), dtype=torch.float32, device=dev)
+                o_l, f_l = mine[: n * D].view(n, D), mine[n * D:].view(n, A)
+                _lib.check(L.vidar_latent_proj_in_forward(_lib.ptr(x_l), _lib.ptr(w_occ), _lib.ptr(b_occ), _lib.ptr(w_feat),
+                                                          _lib.ptr(b_feat), _lib.ptr(o_l), _lib.ptr(f_l), n, E, D, A, st))
+                gathered = torch.empty(world * n * (D + A), dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(gathered, mine, group=group)
+                g2 = gathered.view(world, n * (D + A))
+                occ.view(world, n * D).copy_(g2[:, : n * D])
+                feat.view(world, n * A).copy_(g2[:, n * D:])
+            else:
+                _lib.check(L.vidar_latent_proj_in_forward(_lib.ptr(x_l), _lib.ptr(w_occ), _lib.ptr(b_occ), _lib.ptr(w_feat),
+                                                          _lib.ptr(b_feat), _lib.ptr(occ[c0:c1]), _lib.ptr(feat[c0:c1]), n, E, D, A, st))
+                if world > 1:
+                    dist.all_reduce(flat, group=group)
             _lib.check(L.vidar_latent_prob_forward(_lib.ptr(occ), _lib.ptr(prob), _lib.ptr(aux), bs, D, Hb, Wb,
                                                    int(grid_num), float(grid_step), int(act), c0, n, st))
-            if world > 1:
+            if even:
+                dist.all_gather_into_tensor(prob.view(-1), prob[c0:c1].clone().view(-1), group=group)
+            elif world > 1:
                 dist.all_reduce(prob, group=group)
             _lib.check(L.vidar_latent_pool_forward(_lib.ptr(prob), _lib.ptr(feat), _lib.ptr(pooled), _lib.ptr(aux), bs, D,
                                                    A // D, Hb, Wb, int(grid_num), float(grid_step), float(eps), c0, n, st))
             _lib.check(L.vidar_latent_proj_out_forward(_lib.ptr(pooled[c0:c1]), _lib.ptr(prob[c0:c1]), _lib.ptr(w_b),
                                                        _lib.ptr(b_b), _lib.ptr(out_l), n, E, D, A, st))
-            out = gather_rows(out_l, world, R, group)
-        ctx.save_for_backward(x, occ, feat, prob, pooled, aux, *params)
-        ctx.cfg = (int(grid_num), float(grid_step), float(eps), int(act), group, world, c0, n, (bs, Hb, Wb, E, D, A))
-        return out.view(bs, Hb, Wb, E)
+            out = out_l if rows_io is not None else gather_rows(out_l, world, R, group)
+        ctx.save_for_backward(x_l, occ, feat, prob, pooled, aux, *params)
+        ctx.cfg = (int(grid_num), float(grid_step), float(eps), int(act), group, world, c0, n, (bs, Hb, Wb, E, D, A),
+                   rows_io is not None)
+        return out if rows_io is not None else out.view(bs, Hb, Wb, E)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_out):
         import torch.distributed as dist
         from ..sharding import gather_rows
-        x, occ, feat, prob, pooled, aux, w_occ, b_occ, w_feat, b_feat, w_b, b_b = ctx.saved_tensors
-        grid_num, grid_step, eps, act, group, world, c0, n, (bs, Hb, Wb, E, D, A) = ctx.cfg
+        x_l, occ, feat, prob, pooled, aux, w_occ, b_occ, w_feat, b_feat, w_b, b_b = ctx.saved_tensors
+        grid_num, grid_step, eps, act, group, world, c0, n, (bs, Hb, Wb, E, D, A), rows_io = ctx.cfg
         R, c1 = bs * Hb * Wb, c0 + n
-        dev = x.device
-        g = grad_out.float().contiguous().view(R, E)
+        dev = x_l.device
+        g_l = grad_out.float().contiguous().view(n, E) if rows_io else grad_out.float().contiguous().view(R, E)[c0:c1]
         # parameter gradients in one buffer (one all-reduce when sharded): w_occ b_occ w_feat b_feat w_b b_b
         sizes = [D * E, D, A * E, A, E * A, E]
         pg = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
@@ -224,7 +252,7 @@ class _FusedLatentRendering(torch.autograd.Function):
         L = _lib.lib()
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            _lib.check(L.vidar_latent_proj_out_backward(_lib.ptr(g[c0:c1]), _lib.ptr(pooled[c0:c1]), _lib.ptr(prob[c0:c1]),
+            _lib.check(L.vidar_latent_proj_out_backward(_lib.ptr(g_l), _lib.ptr(pooled[c0:c1]), _lib.ptr(prob[c0:c1]),
                                                         _lib.ptr(w_b), _lib.ptr(b_b), _lib.ptr(g_pooled[c0:c1]), _lib.ptr(g_prob),
                                                         _lib.ptr(g_w_b), _lib.ptr(g_b_b), n, E, D, A, st))
             _lib.check(L.vidar_latent_pool_backward(_lib.ptr(prob), _lib.ptr(feat), _lib.ptr(pooled), _lib.ptr(aux),
@@ -237,15 +265,15 @@ class _FusedLatentRendering(torch.autograd.Function):
                                                     Hb, Wb, grid_num, grid_step, act, c0, n, st))
             if world > 1:
                 dist.all_reduce(grad_occ, group=group)
-            _lib.check(L.vidar_latent_proj_in_backward(_lib.ptr(x[c0:c1]), _lib.ptr(w_occ), _lib.ptr(w_feat),
+            _lib.check(L.vidar_latent_proj_in_backward(_lib.ptr(x_l), _lib.ptr(w_occ), _lib.ptr(w_feat),
                                                        _lib.ptr(grad_occ[c0:c1]), _lib.ptr(gfe[c0:c1]), _lib.ptr(gx_l),
                                                        _lib.ptr(g_w_occ), _lib.ptr(g_b_occ), _lib.ptr(g_w_feat),
                                                        _lib.ptr(g_b_feat), n, E, D, A, st))
             if world > 1:
                 dist.all_reduce(pg, group=group)
-            gx = gather_rows(gx_l, world, R, group)
-        return (gx.view(bs, Hb, Wb, E), g_w_occ.view(D, E), g_b_occ, g_w_feat.view(A, E), g_b_feat, g_w_b.view(E, A), g_b_b,
-                None, None, None, None, None)
+            gx = gx_l if rows_io else gather_rows(gx_l, world, R, group).view(bs, Hb, Wb, E)
+        return (gx, g_w_occ.view(D, E), g_b_occ, g_w_feat.view(A, E), g_b_feat, g_w_b.view(E, A), g_b_b,
+                None, None, None, None, None, None)
 
 
 def fused_projection_supported(E, D, A):
@@ -289,6 +317,18 @@ class LatentRendering(BaseModule):
         self.lora_b = nn.Linear(self.embed_dims // reduction, self.embed_dims)
         self.process_group = None     # set to a process group to shard the BEV cells over its ranks
         self.fuse_projections = True  # False: keep the Linear layers as PyTorch ops around the CUDA core
+
+    def forward_rows(self, embed_rows, bs, bev_h, bev_w, eps=1e-3):
+        """Row-sharded call: `embed_rows` [n, embed_dims] are THIS RANK's rows (`sharding.shard_range` of the
+        bs*bev_h*bev_w BEV rows over `process_group`); returns the same rows of the output.  The small
+        occupancy / feature / prob maps (2.56 MB each) are exchanged inside, the 41 MB grid never is."""
+        head = self.unsup_raymarching_head
+        if not (len(head) == 1 and fused_projection_supported(self.embed_dims, self.pred_height, self.lora_a.out_features)
+                and embed_rows.is_cuda and embed_rows.dtype == torch.float32):
+            raise RuntimeError("forward_rows needs the fused configuration (num_pred_fcs=0, E in {128,256}, 16 feature channels)")
+        return _FusedLatentRendering.apply(embed_rows, head[0].weight, head[0].bias, self.lora_a.weight, self.lora_a.bias,
+                                           self.lora_b.weight, self.lora_b.bias, self.grid_num, self.grid_step, eps,
+                                           _ACT[self.act], self.process_group, (bs, bev_h, bev_w))
 
     def forward(self, embed, eps=1e-3, **kwargs):
         """embed [bs, bev_h, bev_w, embed_dims] -> same shape."""
