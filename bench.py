@@ -10,7 +10,8 @@ A "step" is one pass of ViDAR's two hot paths over one synthetic sample
        (pred_height 16, 256 waypoints of step 0.5, sigmoid; projections fused around the ray-marching core);
   (iii) ViDAR-head ray sampler + cross-entropy forward + backward: sigma [3,16,200,200], 30000
        LiDAR-like rays over 3 frames, 512 waypoints + the GT sample per ray;
-  (iv) voxel ray-caster forward + loss backward (`dvr.render`, L2) on the same volume and rays.
+  (iv) voxel ray-caster forward + loss backward (`dvr.render`, L2) on the same volume and rays, and the
+       dvxlr autograd layer (`DifferentiableVoxelRendering`) forward + backward on them.
 metric = rays/sec = 30000 rays / step time (whole job); ms_per_step is the same thing as time.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -37,10 +38,11 @@ LEVELS = ((116, 200), (58, 100), (29, 50), (15, 25))
 NUM_CAMS, BEV_Q, HEADS, HEAD_DIM, POINTS = 6, 40000, 8, 32, 8
 RAYS, FRAMES, GRID = 30000, 3, (16, 200, 200)
 WAYPOINTS, LR_GRID_NUM, EMBED = 512, 256, 256
-METRIC = "rays/sec (fwd+bwd step: 6-cam 200x200-BEV MSDA + latent rendering + 30k-ray head CE + voxel render)"
+METRIC = "rays/sec (fwd+bwd step: 6-cam 200x200-BEV MSDA + latent rendering + 30k-ray head CE + voxel render + dvxlr layer)"
 WORKLOAD = ("configs[1]+[2]: MSDA fwd+bwd B=6 K=30825 Q=40000 H=8 C=32 L=4 P=8; LatentRendering fwd+bwd "
             "embed[1,200,200,256] pred_height=16 grid_num=256; ray sampler+CE fwd+bwd sigma[3,16,200,200] "
-            "30000 rays x 513 samples; dvr.render(l2) sigma[1,3,16,200,200] 30000 rays")
+            "30000 rays x 513 samples; dvr.render(l2) sigma[1,3,16,200,200] 30000 rays; DifferentiableVoxelRendering "
+            "(dvxlr autograd layer) fwd+bwd on the same rays")
 LR_CFG = dict(type="LatentRendering", embed_dims=EMBED, num_pred_fcs=0, pred_height=GRID[0],
               grid_num=LR_GRID_NUM, grid_step=0.5, reduction=16, act="sigmoid")
 
@@ -212,7 +214,7 @@ def run_ours(args):
     lr0, lr1 = sharding.shard_range(GRID[1] * GRID[2], rank, world)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     names = ["msda_fwd", "msda_bwd", "latent_render", "ray_ce", "render"]
-    ray_grads = torch.empty((2,) + tuple(sigma.shape[1:]), device=dev) if world > 1 else None
+    ray_grads = torch.empty((3,) + tuple(sigma.shape[1:]), device=dev) if world > 1 else None
     marks = []
 
     def msda_stage(gs, group, world_):
@@ -263,17 +265,22 @@ def run_ours(args):
         if record:
             e[4].record()
         pred, gt, grad_sigma = render.dvr.render(sigma, origin, points, tindex, "l2")
-        ce_grad = sg.grad
+        # the dvxlr autograd layer (e2e_predictor_utils.py:91-115): forward + backward of sum(pred)
+        sgd = sigma.detach().requires_grad_(True)
+        dpred, _ = render.DifferentiableVoxelRendering(sgd, origin, points, tindex)
+        dpred.sum().backward()
+        ce_grad, dv_grad = sg.grad, sgd.grad
         if world > 1:
-            # the two ray stages' partial sigma gradients (7.7 MB each) travel in ONE all-reduce
+            # the three ray stages' partial sigma gradients (7.7 MB each) travel in ONE all-reduce
             ray_grads[0].copy_(ce_grad)
             ray_grads[1].copy_(grad_sigma[0])
+            ray_grads[2].copy_(dv_grad[0])
             dist.all_reduce(ray_grads)
-            ce_grad, grad_sigma = ray_grads[0], ray_grads[1][None]
+            ce_grad, grad_sigma, dv_grad = ray_grads[0], ray_grads[1][None], ray_grads[2][None]
         if record:
             e[5].record()
             marks.append(e)
-        return bev.detach(), leaves, pred, grad_sigma, emb.grad, ce_grad
+        return bev.detach(), leaves, pred, grad_sigma, emb.grad, ce_grad, dv_grad
 
     def sync():
         torch.cuda.synchronize()
@@ -516,7 +523,7 @@ def check_sharded(dev, rank, world, grp, last, groups, msda_stage, grad_bev, lat
     import torch.distributed as dist
 
     from vidar_b200 import ray_head, render, sca
-    bev, leaves, pred, grad_sigma, gemb, ce_grad = last
+    bev, leaves, pred, grad_sigma, gemb, ce_grad, dv_grad = last
     full = sca_like_inputs(dev)
     ref_groups = [dict(plan=sca.unit_plan(1, 0, NUM_CAMS)[0], value=full["value"], loc=full["loc"], attn=full["attn"])]
     rbev, rleaves = msda_stage(ref_groups, None, 1)
@@ -550,6 +557,10 @@ def check_sharded(dev, rank, world, grp, last, groups, msda_stage, grad_bev, lat
     ce.sum().backward()
     _, _, rgs = render.dvr.render(sigma, origin, pts, ti, "l2")
     out["ray_ce_grad_sigma"], out["render_grad_sigma"] = rel(ce_grad, sg.grad), rel(grad_sigma, rgs)
+    sgd = sigma.detach().requires_grad_(True)
+    dp, _ = render.DifferentiableVoxelRendering(sgd, origin, pts, ti)
+    dp.sum().backward()
+    out["dvxlr_layer_grad_sigma"] = rel(dv_grad, sgd.grad)
     # LatentRendering: same module without the process group
     pg, latent.process_group = latent.process_group, None
     emb = embed.detach().requires_grad_(True)
@@ -582,7 +593,7 @@ class CpuArm:
                        cost of touching its 31.6 MB value / grad_value);
       LatentRendering  reference formula (torch CPU) on f * 40000 BEV cells;
       head sampler+CE  reference formula (torch CPU) on f * 30000 rays;
-      dvr.render       C/OpenMP port (oracle/dvr_ref.c) on f * 30000 rays.
+      dvr.render + dvxlr layer   C/OpenMP port (oracle/dvr_ref.c) on f * 30000 rays.
     The number of torch threads is calibrated once (more threads than ~32 is slower for these ops on
     many-core hosts)."""
 
@@ -645,7 +656,10 @@ class CpuArm:
         from oracle import dvr_ref
         sigma, origin, points, tindex = self.rays
         t0 = time.perf_counter()
-        dvr_ref.render(sigma, origin, np.ascontiguousarray(points[:, :rays_n]), np.ascontiguousarray(tindex[:, :rays_n]), "l2")
+        pts, ti = np.ascontiguousarray(points[:, :rays_n]), np.ascontiguousarray(tindex[:, :rays_n])
+        dvr_ref.render(sigma, origin, pts, ti, "l2")
+        pred, _ = dvr_ref.dvxlr_forward(sigma, origin, pts, ti)                       # the dvxlr autograd layer
+        dvr_ref.dvxlr_autograd_backward(sigma, origin, pts, ti, np.ones_like(pred))
         return time.perf_counter() - t0
 
     def step(self, f):
@@ -678,7 +692,7 @@ class CpuArm:
         txt = (f"each step = fraction f={f:.3f} of every stage on {self.threads} torch threads / {dvr_ref.num_threads()} OpenMP "
                f"threads: MSDA fwd+bwd (torch CPU grid_sample formula = the reference's CPU path) 6 cameras x {int(BEV_Q * f)} "
                f"queries; LatentRendering core (reference formula) {int(GRID[1] * GRID[2] * f)} cells; head ray sampler+CE "
-               f"(reference formula) {int(RAYS * f)} rays; C/OpenMP port of dvr.render {int(RAYS * f)} rays.  Mean seconds per "
+               f"(reference formula) {int(RAYS * f)} rays; C/OpenMP port of dvr.render and of the dvxlr layer {int(RAYS * f)} rays.  Mean seconds per "
                "sample-step by stage: " + ", ".join(f"{k}={v:.2f}" for k, v in r["parts"].items())
                + f"; rays/s = f*{RAYS}/t_sample")
         if "full_step_s" in r:

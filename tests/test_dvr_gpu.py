@@ -232,3 +232,26 @@ def test_large_grid_needs_shared_memory_opt_in_for_both_kernels(cuda):
     pred2, gt2, grad = render.dvr.render(s, o, p, t, "l2")
     _close(pred2, rp2, "pred (large grid, render)", rtol=1e-5)
     _close(grad, rgrad, "grad_sigma (large grid)")
+
+
+def test_tie_prone_rays_equal_reference_cuda_golden(cuda):
+    """The tie-prone rays against what the REFERENCE's own CUDA binary returned for them
+    (tests/golden/dvr_ties.npz, tools/make_golden_dvr.py): pred / gt of render_forward, render and the dvxlr
+    autograd forward, every ray."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dvr_ties.npz"))
+    s, o, p, t = _t(cuda, g["sigma"], g["origin"], g["points"], g["tindex"])
+    grid = list(g["sigma"].shape[1:])
+    for ph in ("test", "train"):
+        pred, gt = render.dvr.render_forward(s, o, p, t, grid, ph)
+        _close(pred, g[f"fwd_{ph}_pred"], f"render_forward {ph} pred", rtol=1e-5)
+        _close(gt, g[f"fwd_{ph}_gt"], f"render_forward {ph} gt", rtol=1e-5)
+    pred, gt, _ = render.dvr.render(s, o, p, t, "l1")
+    _close(pred, g["render_l1_pred"], "render pred", rtol=1e-5)
+    sg = s.clone().requires_grad_(True)
+    pr, gtd = render.DifferentiableVoxelRendering(sg, o, p, t)
+    _close(pr, g["dvxlr_pred"], "dvxlr pred", rtol=1e-5)
+    _close(gtd, g["dvxlr_gt"], "dvxlr gt", rtol=1e-5)
+    gp = torch.from_numpy(g["grad_pred"]).to(cuda)
+    pr.backward(gp)
+    _close(sg.grad, g["scatter_grad_sigma_v1"], "dvxlr autograd grad_sigma vs the reference's list scatter")

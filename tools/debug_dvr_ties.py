@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import build_ref, dvr_ref
 from tests.inputs import dvr_inputs_ties
 from vidar_b200 import render
-sigma, origin, points, tindex = dvr_inputs_ties(M=3000)
+sigma, origin, points, tindex = dvr_inputs_ties(M=int(os.environ.get('TIES_M', '6000')))
 dev = torch.device("cuda:0")
 s, o, p, t = (torch.from_numpy(a).to(dev) for a in (sigma, origin, points, tindex))
 grid = list(sigma.shape[1:])
@@ -20,5 +20,6 @@ for name, f_gpu, f_orc, f_ref in (
          lambda: ref.render(s, o, p, t, "l1")[0])):
     g, orc, r = f_gpu().cpu().numpy()[0], f_orc()[0], f_ref().cpu().numpy()[0]
     out[name] = {"gpu_vs_ref": bad(g, r).tolist()[:20], "oracle_vs_ref": bad(orc, r).tolist()[:20], "gpu_vs_oracle": bad(g, orc).tolist()[:20],
-                 "frames_of_gpu_vs_ref": tindex[0, bad(g, r)].tolist()[:20]}
+                 "frames_of_gpu_vs_ref": tindex[0, bad(g, r)].tolist()[:20],
+                 "detail": [dict(i=int(i), point=points[0, i].tolist(), gpu=float(g[i]), oracle=float(orc[i]), ref=float(r[i])) for i in sorted(set(bad(g, orc).tolist() + bad(g, r).tolist()))[:12]]}
 print(json.dumps(out))

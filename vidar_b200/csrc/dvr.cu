@@ -395,41 +395,70 @@ __device__ __forceinline__ int crossings_before(double T, double tMax0, double t
   return q >= (double)hi ? hi : (int)q;
 }
 
-template <int V>
+// One ray by one thread, bit-faithful: the fallback of the warp-per-ray kernels.
+//   MODE 0: forward (pred, gt; `mode` = train phase)      MODE 1: dvr.render (loss gradient; `mode` = loss type)
+//   MODE 2: fused backward of DifferentiableVoxelRendering[V2] (external grad_pred / grad_ray_pred)
+template <int V, int MODE>
 __device__ void serial_ray(const Grid& G, const Ray& r, const float* __restrict__ sigma,
                            float* __restrict__ pred_dist, float* __restrict__ gt_dist,
-                           float* __restrict__ grad_sigma, int n, int c, int mode, bool grad) {
+                           float* __restrict__ grad_sigma, int n, int c, int mode,
+                           const float* __restrict__ grad_pred, const float* __restrict__ grad_ray_pred,
+                           float* __restrict__ grad_sigma_regul, int max_d) {
+  constexpr bool MERGE = Traits<V>::kMerge;
   const size_t vol = (size_t)G.Z * G.Y * G.X;
   const size_t foff = ((size_t)n * G.T + r.ts) * vol;
   Composite comp;
   {
-    Segmenter<false, Composite> seg(sigma + foff, G.Y, G.X, comp);
+    Segmenter<MERGE, Composite> seg(sigma + foff, G.Y, G.X, comp);
     walk<V>(G, r, seg);
+    seg.finish();
   }
   if (comp.count == 0) return;
   const double exp_d = comp.pred();
-  double gt = r.gt_d;
-  if (grad || mode == 1) gt = fmin(gt, comp.d_last);
-  pred_dist[(size_t)n * G.M + c] = (float)exp_d;
-  gt_dist[(size_t)n * G.M + c] = (float)gt;
-  if (!grad) return;
-  double dl_dd = 1.0;
-  if (mode == 0) dl_dd = (exp_d >= gt) ? 1 : -1;
-  else if (mode == 1) dl_dd = (exp_d - gt);
-  else if (mode == 2) dl_dd = (exp_d >= gt) ? (1.0 / gt) : -(1.0 / gt);
-  RenderGradSink sink{grad_sigma + foff, G.Y, G.X, comp.S0, dl_dd};
-  Segmenter<false, RenderGradSink> seg(sigma + foff, G.Y, G.X, sink);
-  walk<V>(G, r, seg);
+  const size_t ray = (size_t)n * G.M + c;
+  if (MODE != 2) {
+    double gt = r.gt_d;
+    if (MODE == 1 || MERGE || mode == 1) gt = fmin(gt, comp.d_last);
+    pred_dist[ray] = (float)exp_d;
+    gt_dist[ray] = (float)gt;
+    if (MODE == 0) return;
+    double dl_dd = 1.0;
+    if (mode == 0) dl_dd = (exp_d >= gt) ? 1 : -1;
+    else if (mode == 1) dl_dd = (exp_d - gt);
+    else if (mode == 2) dl_dd = (exp_d >= gt) ? (1.0 / gt) : -(1.0 / gt);
+    RenderGradSink sink{grad_sigma + foff, G.Y, G.X, comp.S0, dl_dd};
+    Segmenter<MERGE, RenderGradSink> seg(sigma + foff, G.Y, G.X, sink);
+    walk<V>(G, r, seg);
+    seg.finish();
+  } else {
+    const bool v2 = grad_ray_pred != nullptr;
+    ScatterSink sink{grad_sigma + foff, v2 ? grad_ray_pred + ray * max_d : nullptr, v2 ? grad_sigma_regul + foff : nullptr,
+                     G.Y, G.X, max_d, comp.S0, (double)grad_pred[ray], !v2};
+    Segmenter<MERGE, ScatterSink> seg(sigma + foff, G.Y, G.X, sink);
+    walk<V>(G, r, seg);
+    seg.finish();
+  }
 }
 
-// mode: GRAD ? loss_type : train_phase
-template <int V, bool GRAD>
+// MODE as in serial_ray.  mode: MODE 1 ? loss_type : train_phase.  Merge variants (dvxlr): a run of
+// consecutive records with the same (rounded) voxel is ONE segment -- length from the crossing before the
+// run to the run's last crossing (dvxlr.cu:366-373) -- carried by the run's last record; run heads are
+// found with a warp max-scan, list ordinals (the MAX_D cap, grad_ray_pred slots) with an add-scan.
+struct WarpRayExtra {
+  const float* grad_pred;       // MODE 2: [N, M]
+  const float* grad_ray_pred;   // MODE 2, v2: [N, M, max_d] or nullptr
+  float* grad_sigma_regul;      // MODE 2, v2
+  int max_d;
+};
+template <int V, int MODE>
 __global__ void __launch_bounds__(kWarpRaysPerBlock * 32)
 render_warp_kernel(Grid G, const float* __restrict__ sigma, const float* __restrict__ origin,
                    const float* __restrict__ points, const float* __restrict__ tindex,
                    float* __restrict__ pred_dist, float* __restrict__ gt_dist,
-                   float* __restrict__ grad_sigma, int mode, int cap, double kTieEps) {
+                   float* __restrict__ grad_sigma, int mode, int cap, double kTieEps, WarpRayExtra ex) {
   using TR = Traits<V>;
+  constexpr bool GRAD = MODE != 0;
+  constexpr bool MERGE = TR::kMerge;
   extern __shared__ double smem_d[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y;
@@ -464,7 +493,7 @@ render_warp_kernel(Grid G, const float* __restrict__ sigma, const float* __restr
   }
   eligible = eligible && bound > 0 && bound <= cap && isfinite(r.gt_d) && r.gt_d > 0;
   if (!eligible) {
-    if (lane == 0) serial_ray<V>(G, r, sigma, pred_dist, gt_dist, grad_sigma, n, c, mode, GRAD);
+    if (lane == 0) serial_ray<V, MODE>(G, r, sigma, pred_dist, gt_dist, grad_sigma, n, c, mode, ex.grad_pred, ex.grad_ray_pred, ex.grad_sigma_regul, ex.max_d);
     return;
   }
   // ---- phase 1: slices of the parameter range
@@ -551,7 +580,7 @@ render_warp_kernel(Grid G, const float* __restrict__ sigma, const float* __restr
     }
   }
   if (__any_sync(0xffffffffu, tie)) {
-    if (lane == 0) serial_ray<V>(G, r, sigma, pred_dist, gt_dist, grad_sigma, n, c, mode, GRAD);
+    if (lane == 0) serial_ray<V, MODE>(G, r, sigma, pred_dist, gt_dist, grad_sigma, n, c, mode, ex.grad_pred, ex.grad_ray_pred, ex.grad_sigma_regul, ex.max_d);
     return;
   }
   __syncwarp();
@@ -560,24 +589,40 @@ render_warp_kernel(Grid G, const float* __restrict__ sigma, const float* __restr
   const size_t foff = ((size_t)n * G.T + r.ts) * vol;
   const float* sg = sigma + foff;
   double carry_csd = 0.0, carry_U = 0.0, T_carry = 1.0, pred_part = 0.0, d_last = 0.0;
+  int carry_head = 0;                                   // MERGE: record index of the current run's head
   for (int base = 0; base < N; base += 32) {
     const int k = base + lane;
     const bool valid = k < N;
     const int idx = valid ? vxs[k] : -1;
     const bool ins = idx >= 0;
     const double tk = valid ? ts[k] : 0.0;
-    const double tp = (valid && k > 0) ? ts[k - 1] : 0.0;
-    const double dt = ins ? fmax(0.0, tk - tp) : 0.0;
-    const double sd = ins ? (double)__ldg(sg + idx) * dt : 0.0;
+    bool tail = ins;                                     // does this record close a segment?
+    double t0 = (valid && k > 0) ? ts[k - 1] : 0.0;      // parameter at which its segment starts
+    int hs = k;
+    if (MERGE) {
+      const bool head = ins && (k == 0 || vxs[k - 1] != idx);
+      tail = ins && (k == N - 1 || vxs[k + 1] != idx);
+      hs = head ? k : -1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, hs, o);
+        if (lane >= o) hs = max(hs, u);
+      }
+      hs = max(hs, carry_head);
+      carry_head = __shfl_sync(0xffffffffu, hs, 31);
+      t0 = (hs > 0) ? ts[hs - 1] : 0.0;
+    }
+    const double dt = tail ? fmax(0.0, tk - t0) : 0.0;
+    const double sd = tail ? (double)__ldg(sg + idx) * dt : 0.0;
     const double csd = warp_incl_scan(sd, lane) + carry_csd;
     const double T = exp(-csd);
     double Tp = __shfl_up_sync(0xffffffffu, T, 1);
     if (lane == 0) Tp = T_carry;
-    if (ins) {
+    if (tail) {
       pred_part += (Tp - T) * tk;
       d_last = fmax(d_last, tk);
     }
-    const double term = (ins && k > 0) ? Tp * (tk - tp) : 0.0;
+    const double term = (tail && hs > 0) ? Tp * (tk - t0) : 0.0;      // T_prev (d_i - d_{i-1}), first segment: 0
     const double U = warp_incl_scan(term, lane) + carry_U;
     if (GRAD && valid) us[k] = U;
     carry_csd = __shfl_sync(0xffffffffu, csd, 31);
@@ -591,26 +636,69 @@ render_warp_kernel(Grid G, const float* __restrict__ sigma, const float* __restr
   }
   const double exp_d = pred_part + T_carry * d_last;    // + p_out * max_d
   double gt = r.gt_d;
-  if (GRAD || mode == 1) gt = fmin(gt, d_last);
-  if (lane == 0) {
+  if (MODE == 1 || MERGE || mode == 1) gt = fmin(gt, d_last);
+  if (MODE != 2 && lane == 0) {
     pred_dist[(size_t)n * G.M + c] = (float)exp_d;
     gt_dist[(size_t)n * G.M + c] = (float)gt;
   }
   if (!GRAD) return;
-  // ---- phase 3: loss gradient
-  double dl_dd = 1.0;
-  if (mode == 0) dl_dd = (exp_d >= gt) ? 1 : -1;
-  else if (mode == 1) dl_dd = (exp_d - gt);
-  else if (mode == 2) dl_dd = (exp_d >= gt) ? (1.0 / gt) : -(1.0 / gt);
+  // ---- phase 3: gradient emission, one record per lane
+  const size_t ray = (size_t)n * G.M + c;
+  double coef = 1.0;
+  if (MODE == 1) {
+    if (mode == 0) coef = (exp_d >= gt) ? 1 : -1;
+    else if (mode == 1) coef = (exp_d - gt);
+    else if (mode == 2) coef = (exp_d >= gt) ? (1.0 / gt) : -(1.0 / gt);
+  }
+  const float coef_f = (MODE == 2) ? __ldg(ex.grad_pred + ray) : 0.f;
+  const float* grp = (MODE == 2 && ex.grad_ray_pred) ? ex.grad_ray_pred + ray * ex.max_d : nullptr;
   float* gs = grad_sigma + foff;
+  float* gsr = grp ? ex.grad_sigma_regul + foff : nullptr;
   const double S0 = carry_U;
   __syncwarp();
-  for (int k = lane; k < N; k += 32) {
-    const int idx = vxs[k];
-    if (idx < 0) continue;
-    const double dt = fmax(0.0, ts[k] - (k > 0 ? ts[k - 1] : 0.0));
-    const float g = (float)(dl_dd * (-dt * (S0 - us[k])));
-    if (g != 0.f) red_add_f32(gs + idx, g);
+  carry_head = 0;
+  int carry_ord = 0;                                     // segments closed before this chunk
+  for (int base = 0; base < N; base += 32) {
+    const int k = base + lane;
+    const bool valid = k < N;
+    const int idx = valid ? vxs[k] : -1;
+    const bool ins = idx >= 0;
+    bool tail = ins;
+    double t0 = (valid && k > 0) ? ts[k - 1] : 0.0;
+    if (MERGE) {
+      const bool head = ins && (k == 0 || vxs[k - 1] != idx);
+      tail = ins && (k == N - 1 || vxs[k + 1] != idx);
+      int hs = head ? k : -1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, hs, o);
+        if (lane >= o) hs = max(hs, u);
+      }
+      hs = max(hs, carry_head);
+      carry_head = __shfl_sync(0xffffffffu, hs, 31);
+      t0 = (hs > 0) ? ts[hs - 1] : 0.0;
+    }
+    int ord = 0;                                         // list slot of this segment (MODE 2: MAX_D cap, v2 slots)
+    if (MODE == 2) {
+      const unsigned tb = __ballot_sync(0xffffffffu, tail);
+      ord = carry_ord + __popc(tb & ((1u << lane) - 1u));
+      carry_ord += __popc(tb);
+    }
+    if (!tail) continue;
+    const double dt = fmax(0.0, ts[k] - t0);
+    if (MODE == 1) {
+      const float g = (float)(coef * (-dt * (S0 - us[k])));
+      if (g != 0.f) red_add_f32(gs + idx, g);
+    } else if (ord < ex.max_d) {
+      // float(dd) * float(grad) like `gradpred[..., None] * dd_dsigma` on fp32 tensors (e2e_predictor_utils.py:106)
+      float g = (float)(-dt * (S0 - us[k])) * coef_f;
+      if (!grp && isnan(g)) g = 0.f;                     // v1: nan_to_num (:107-108)
+      if (g != 0.f) red_add_f32(gs + idx, g);
+      if (grp) {
+        const float gr = __ldg(grp + ord);
+        if (gr != 0.f) red_add_f32(gsr + idx, gr);
+      }
+    }
   }
 }
 
@@ -789,10 +877,10 @@ extern "C" int vidar_dvr_render_forward(const float* sigma, const float* origin,
   if (M == 0) return VIDAR_OK;
   int cap;
   size_t smem;
-  if (warp_ray_config(G, render_warp_kernel<V_DVR_FWD, false>, cap, smem)) {
-    render_warp_kernel<V_DVR_FWD, false><<<ray_grid(G, kWarpRaysPerBlock), kWarpRaysPerBlock * 32, smem,
-                                           (cudaStream_t)stream>>>(G, sigma, origin, points, tindex, pred_dist,
-                                                                   gt_dist, nullptr, train_phase, cap, tie_eps());
+  if (warp_ray_config(G, render_warp_kernel<V_DVR_FWD, 0>, cap, smem)) {
+    render_warp_kernel<V_DVR_FWD, 0><<<ray_grid(G, kWarpRaysPerBlock), kWarpRaysPerBlock * 32, smem,
+                                       (cudaStream_t)stream>>>(G, sigma, origin, points, tindex, pred_dist,
+                                                               gt_dist, nullptr, train_phase, cap, tie_eps(), WarpRayExtra{});
   } else {
     forward_kernel<V_DVR_FWD><<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
         G, sigma, origin, points, tindex, pred_dist, gt_dist, train_phase);
@@ -813,10 +901,10 @@ extern "C" int vidar_dvr_render(const float* sigma, const float* origin, const f
   if (M == 0) return VIDAR_OK;
   int cap;
   size_t smem;
-  if (warp_ray_config(G, render_warp_kernel<V_DVR_RENDER, true>, cap, smem)) {
-    render_warp_kernel<V_DVR_RENDER, true><<<ray_grid(G, kWarpRaysPerBlock), kWarpRaysPerBlock * 32, smem,
-                                             (cudaStream_t)stream>>>(G, sigma, origin, points, tindex, pred_dist,
-                                                                     gt_dist, grad_sigma, loss_type, cap, tie_eps());
+  if (warp_ray_config(G, render_warp_kernel<V_DVR_RENDER, 1>, cap, smem)) {
+    render_warp_kernel<V_DVR_RENDER, 1><<<ray_grid(G, kWarpRaysPerBlock), kWarpRaysPerBlock * 32, smem,
+                                          (cudaStream_t)stream>>>(G, sigma, origin, points, tindex, pred_dist,
+                                                                  gt_dist, grad_sigma, loss_type, cap, tie_eps(), WarpRayExtra{});
   } else {
     render_grad_kernel<<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
         G, sigma, origin, points, tindex, pred_dist, gt_dist, grad_sigma, loss_type);
@@ -833,8 +921,16 @@ extern "C" int vidar_dvxlr_forward(const float* sigma, const float* origin, cons
   VIDAR_REQUIRE(sigma && origin && points && tindex && pred_dist && gt_dist,
                 "dvxlr.forward: null pointer argument");
   if (M == 0) return VIDAR_OK;
-  forward_kernel<V_DVXLR><<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
-      G, sigma, origin, points, tindex, pred_dist, gt_dist, 1);
+  int cap;
+  size_t smem;
+  if (warp_ray_config(G, render_warp_kernel<V_DVXLR, 0>, cap, smem)) {
+    // one ray per warp; consecutive records of one (rounded) voxel merge into a segment by a warp scan
+    render_warp_kernel<V_DVXLR, 0><<<ray_grid(G, kWarpRaysPerBlock), kWarpRaysPerBlock * 32, smem, (cudaStream_t)stream>>>(
+        G, sigma, origin, points, tindex, pred_dist, gt_dist, nullptr, 1, cap, tie_eps(), WarpRayExtra{});
+  } else {
+    forward_kernel<V_DVXLR><<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
+        G, sigma, origin, points, tindex, pred_dist, gt_dist, 1);
+  }
   return check_launch("dvxlr.forward");
 }
 
@@ -897,8 +993,16 @@ extern "C" int vidar_dvxlr_backward_fused(const float* sigma, const float* origi
                 "dvxlr.backward_fused: grad_ray_pred and grad_sigma_regul go together");
   VIDAR_REQUIRE(max_d > 0, "dvxlr.backward_fused: max_d must be positive");
   if (M == 0) return VIDAR_OK;
-  dvxlr_fused_bwd_kernel<<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
-      G, sigma, origin, points, tindex, grad_pred, grad_ray_pred, grad_sigma, grad_sigma_regul,
-      max_d);
+  int cap;
+  size_t smem;
+  if (warp_ray_config(G, render_warp_kernel<V_DVXLR, 2>, cap, smem)) {
+    render_warp_kernel<V_DVXLR, 2><<<ray_grid(G, kWarpRaysPerBlock), kWarpRaysPerBlock * 32, smem, (cudaStream_t)stream>>>(
+        G, sigma, origin, points, tindex, nullptr, nullptr, grad_sigma, 1, cap, tie_eps(),
+        WarpRayExtra{grad_pred, grad_ray_pred, grad_sigma_regul, max_d});
+  } else {
+    dvxlr_fused_bwd_kernel<<<ray_grid(G, kRayBlock), kRayBlock, 0, (cudaStream_t)stream>>>(
+        G, sigma, origin, points, tindex, grad_pred, grad_ray_pred, grad_sigma, grad_sigma_regul,
+        max_d);
+  }
   return check_launch("dvxlr.backward_fused");
 }

@@ -65,17 +65,27 @@ class ViDARRayHead:
                            pred_frame_num, bev_h, bev_w, pc_range):
         valid_frame_num, inter_num, bs, token_num, num_height_pred = bev_preds.shape
         frames = [i for i in range(start_idx, pred_frame_num) if i in valid_frames]
-        batched = []
+        # The reference selects every frame's points with a boolean mask (a host sync per (batch, frame)),
+        # concatenates them in frame order and NaN-pads to the longest sample (:239-262).  Same rays, same
+        # order, no sync: a stable sort by the frame's position in `frames`; points of other frames become
+        # padding (NaN coordinates, tindex -1) at the tail instead of being dropped -- every consumer skips
+        # padded rays, so only the padded length differs (it is the input length, known on the host).
+        max_pts = max(int(p.shape[0]) for p in gt_points[:bs])
+        pts = bev_preds.new_full((bs, max_pts, 3), float("nan"))
+        tindex = bev_preds.new_full((bs, max_pts), -1.0)
         for b in range(bs):
             cur = gt_points[b]
-            batched.append(torch.cat([cur[cur[:, -1] == i] for i in frames], 0))
-        max_pts = max(p.shape[0] for p in batched)
+            f = cur[:, -1]
+            key = torch.full_like(f, float(len(frames)))
+            for r, i in enumerate(frames):
+                key = torch.where(f == i, torch.full_like(f, float(r)), key)
+            order = torch.argsort(key, stable=True)
+            keep = (key[order] < len(frames))
+            srt = cur[order]
+            pts[b, : cur.shape[0]] = torch.where(keep[:, None], srt[:, :3].to(pts.dtype), pts.new_tensor(float("nan")))
+            tindex[b, : cur.shape[0]] = torch.where(keep, srt[:, -1].to(pts.dtype) - start_idx, pts.new_tensor(-1.0))
         if batched_origin_points is None:
             batched_origin_points = torch.zeros((bs, len(valid_frames), 3), dtype=bev_preds.dtype, device=bev_preds.device)
-        pts = torch.stack([F.pad(p, (0, 0, 0, max_pts - len(p)), mode="constant", value=float("nan")) for p in batched])
-        tindex = pts[..., -1].contiguous() - start_idx
-        tindex[torch.isnan(tindex)] = -1
-        pts = pts[..., :3].contiguous()
         origin_grids = bev_geometry.coords_to_voxel_grids(batched_origin_points, bev_h=bev_h, bev_w=bev_w,
                                                           pillar_num=num_height_pred, pc_range=pc_range)
         gt_grids = bev_geometry.coords_to_voxel_grids(pts, bev_h=bev_h, bev_w=bev_w, pillar_num=num_height_pred,
