@@ -47,11 +47,19 @@ LR_CFG = dict(type="LatentRendering", embed_dims=EMBED, num_pred_fcs=0, pred_hei
               grid_num=LR_GRID_NUM, grid_step=0.5, reduction=16, act="sigmoid")
 
 
+def set_workload(bev=200, rays=30000, frames=3):
+    """configs[4] sweep (tools/sweep_multi.py): resize the step -- BEV bev x bev queries / cells / volume,
+    `rays` LiDAR rays over `frames` frames.  The headline line always uses the defaults."""
+    global BEV_Q, RAYS, FRAMES, GRID
+    BEV_Q, RAYS, FRAMES, GRID = bev * bev, rays, frames, (16, bev, bev)
+
+
 # ------------------------------------------------------------------------------------------
 # synthetic inputs
 # ------------------------------------------------------------------------------------------
-def sca_like_inputs(device, cams=NUM_CAMS, Q=BEV_Q, seed=0):
+def sca_like_inputs(device, cams=NUM_CAMS, Q=None, seed=0):
     from vidar_b200 import synthetic
+    Q = BEV_Q if Q is None else Q
     return synthetic.sca_like_inputs(device, cams=cams, Q=Q, seed=seed, levels=LEVELS, heads=HEADS,
                                      head_dim=HEAD_DIM, points=POINTS)
 
@@ -79,6 +87,11 @@ def msda_algorithmic_bytes(rows, cams_touched):
     fwd = cams_touched * value + rows * 4096
     bwd = cams_touched * 3 * value + rows * 7168
     return fwd, bwd
+
+
+def msda_algorithmic_bytes_q(rows, cams_touched, queries):
+    """as msda_algorithmic_bytes; `queries` is unused (per-row bytes do not depend on the BEV size)."""
+    return msda_algorithmic_bytes(rows, cams_touched)
 
 
 class ClockSampler:
@@ -141,6 +154,16 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+_CAM_GROUPS = {}
+
+
+def _camera_groups(world, rank):
+    from vidar_b200 import sca
+    if world not in _CAM_GROUPS:
+        _CAM_GROUPS[world] = sca.camera_groups(world, NUM_CAMS, rank)
+    return _CAM_GROUPS[world]
+
+
 def bench_config(world):
     """The `config` object of the JSON line -- identical for the GPU arm and the reference arm."""
     return {"workload": WORKLOAD,
@@ -152,7 +175,7 @@ def bench_config(world):
                          "LatentRendering: BEV rows/cells split over ranks, row-sharded in/out (all-gather of the 2.56 MB maps only)") if world > 1 else "single GPU"}
 
 
-def run_ours(args):
+def run_ours(args, light=False):
     import torch.distributed as dist
 
     from vidar_b200 import _lib, ray_head, render, sca, sharding
@@ -168,13 +191,14 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     grp = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
         grp = dist.group.WORLD
 
     # ---- device-resident inputs (this rank's shard): the product's own unit plan decides who owns what
     full = sca_like_inputs(dev)
     plan = sca.unit_plan(world, rank, NUM_CAMS)
-    cam_groups = sca.camera_groups(world, NUM_CAMS, rank) if world > 1 else {}
+    cam_groups = _camera_groups(world, rank) if world > 1 else {}
     groups = []
     for cam0, ncl, S, lo, hi in plan:
         sl = slice(cam0, cam0 + ncl)
@@ -347,8 +371,14 @@ def run_ours(args):
             last = step(True)
         sync()
         launches = _lib.launch_count() - n1     # launches of K steps (a replayed graph does not pass through the C entry points)
-    parts = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, n in enumerate(names)}
+    # median over the steps: the first eagerly launched step after a graph capture pays one-off allocations
+    parts = {n: float(np.median([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, n in enumerate(names)}
 
+    if light:                                          # sweep: timing only
+        if clocks is None and rank == 0:
+            clocks = {}
+        return {"ms_per_step": ms_step, "rays_per_s": RAYS / (ms_step * 1e-3), "breakdown_ms": parts, "launch_mode": mode,
+                "rows_this_rank": rows}
     if os.environ.get("VIDAR_BENCH_PROFILE") == "1":   # under ncu: kernels only
         # one more step inside a cudaProfilerStart/Stop range: `ncu --profile-from-start off`
         # captures exactly this step's kernels (tools/profile_round.sh)

@@ -145,6 +145,14 @@ int vidar_msda_sca_rows_backward(const float* value, const int64_t* spatial_shap
                                  float* grad_logits, int bs, int ncl, int cam0, int K, int H, int C, int L,
                                  int Qrows, int Qd, int P, int D, int S, int s_lo, int s_hi, void* stream);
 
+/* (i-c) The Linear layer in front of the sampling: value_proj of MSDeformableAttention3D
+ * (spatial_cross_attention.py:333) over the flattened camera features (modules/transformer.py:159-179),
+ * y [M, N] = x [M, K] w[N, K]^T + bias[N], fp32 in / out.  tcgen05 tensor cores with a 3xTF32 split (fp32
+ * accuracy, ~1e-6 relative: a plain TF32 GEMM would miss the 1e-4 parity bar), operands by TMA, accumulator in
+ * TMEM.  K % 32 == 0, N % 128 == 0; bias may be NULL.  w_split: 2*N*K floats of caller-owned scratch. */
+int vidar_linear_tf32x3(const float* x, const float* w, const float* bias, float* y, float* w_split,
+                        int M, int N, int K, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (ii-a) dvr / dvxlr / dvxlr_v2 voxel ray-casters
  *   sigma   [N, T, Z, Y, X]   (reference names the dims H, L, W)

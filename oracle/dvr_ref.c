@@ -93,7 +93,11 @@ static int trace_ray(const dims_t* D, int variant, const float* sigma, const flo
   int vx = (int)xo, vy = (int)yo, vz = (int)zo;
   double fx = (double)vx, fy = (double)vy, fz = (double)vz; /* running "path" position */
   const double rx = xe - xo, ry = ye - yo, rz = ze - zo;
-  const double gt_d = sqrt(rx * rx + ry * ry + rz * rz);
+  /* nvcc (default -fmad=true) contracts the reference's `rx*rx + ry*ry + rz*rz` into two fused
+   * multiply-adds (order read off the SASS of the same expression); the last bit of the norm -- hence of the direction -- decides round() ties on
+   * lattice-aligned rays (half-integer origins: every crossing).  Pinned by tests/golden/dvr_ties.npz
+   * (the reference's own CUDA binary). */
+  const double gt_d = sqrt(fma(rz, rz, fma(rx, rx, ry * ry)));     /* SASS: DMUL ry,ry ; DFMA rx,rx ; DFMA rz,rz */
   out->gt_raw = gt_d;
   const double dx = rx / gt_d, dy = ry / gt_d, dz = rz / gt_d;
   const int sx = (dx >= 0) ? 1 : -1, sy = (dy >= 0) ? 1 : -1, sz = (dz >= 0) ? 1 : -1;
