@@ -26,7 +26,7 @@ CASES = {
     "cfg1_frac": lambda: dvr_inputs_cfg1(seed=0, integer_origin=False),
     "lidar_small": lambda: dvr_inputs_lidar(M=1500, T=2, grid=(8, 64, 64), seed=5, pad=12),
     "outside": lambda: dvr_inputs_outside(zero_length=False),
-    "ties": lambda: dvr_inputs_ties(M=3000),
+    "ties": lambda: dvr_inputs_ties(M=6000),
 }
 
 

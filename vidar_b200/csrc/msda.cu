@@ -1128,6 +1128,9 @@ extern "C" int vidar_msda_rows_forward(const float* value, const int64_t* spatia
   rc = fill_rows(p, idx, count, inv_count, bs, ncl, cam0, Qd, S, s_lo, s_hi, who);
   if (rc) return rc;
   VIDAR_REQUIRE(slots, "%s: null output", who);
+  // the streaming hint helps the plain forward (2.24 -> 2.06 ms) but not this one, whose epilogue also sends 245 MB
+  // of slot reductions through L2 (2.25 -> 2.35 ms, gpurun r2g): plain loads here
+  p.na_bytes = 0xffffffffu;
   if (slab_ok(p) && slab_forward_on()) return launch_slab_forward<false, true>(p, slots, (cudaStream_t)stream, who);
   VIDAR_ROWS_LAUNCH(msda_forward_kernel, false, p, slots);
   return check_launch(who);
@@ -1168,6 +1171,7 @@ extern "C" int vidar_msda_sca_rows_forward(const float* value, const int64_t* sp
   rc = fill_rows(p, idx, count, inv_count, bs, ncl, cam0, Qd, S, s_lo, s_hi, who);
   if (rc) return rc;
   VIDAR_REQUIRE(slots, "%s: null output", who);
+  p.na_bytes = 0xffffffffu;
   if (slab_ok(p) && slab_forward_on()) return launch_slab_forward<true, true>(p, slots, (cudaStream_t)stream, who);
   VIDAR_ROWS_LAUNCH(msda_forward_kernel, true, p, slots);
   return check_launch(who);

@@ -22,11 +22,24 @@ import warnings
 import torch
 import torch.nn as nn
 
+from .. import linear as _tc
 from ..msda import MSDeformAttn3DFusedFunction, MultiScaleDeformableAttnFunction_fp32
 from ..registry import ATTENTION, BaseModule, build_attention, constant_init, xavier_init
 
 msda_apply = MultiScaleDeformableAttnFunction_fp32.apply
 msda3d_fused_apply = MSDeformAttn3DFusedFunction.apply
+
+
+TC_LINEAR = True      # Linear layers of these modules on the tensor cores (3xTF32, vidar_b200/linear.py) when the shape allows
+
+
+def _linear(layer, x):
+    """`layer(x)` for an nn.Linear: the tcgen05 3xTF32 kernel (fp32-accurate) for fp32 CUDA inputs whose in / out
+    features are multiples of 128 -- value_proj over 6 x 30825 rows is the one large GEMM on the path
+    (spatial_cross_attention.py:333) -- otherwise the module itself (cuBLAS)."""
+    if TC_LINEAR and layer.bias is not None and _tc.supported(layer.in_features, layer.out_features, x) and x.numel() > 0:
+        return _tc.linear_tf32x3(x, layer.weight, layer.bias)
+    return layer(x)
 
 
 def _check_heads(embed_dims, num_heads):
@@ -101,7 +114,7 @@ class MSDeformableAttention3D(BaseModule):
         assert (spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum() == num_value
         H, L, P = self.num_heads, self.num_levels, self.num_points
 
-        value = self.value_proj(value)
+        value = _linear(self.value_proj, value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, H, -1)
@@ -236,10 +249,10 @@ class SpatialCrossAttention(BaseModule):
             from .. import sharding
             bs, Q, C = slots.shape
             rows = sharding.reduce_scatter_rows(slots.reshape(bs * Q, C), self.process_group)     # this rank's pillars
-            rows = self.dropout(self.output_proj(rows))
+            rows = self.dropout(_linear(self.output_proj, rows))
             full = sharding.all_gather_rows(rows, bs * Q, self.process_group).view(bs, Q, C)       # the BEV grid
             return full + inp_residual          # the residual stays replicated (its gradient is the full one)
-        return self.dropout(self.output_proj(slots)) + inp_residual
+        return self.dropout(_linear(self.output_proj, slots)) + inp_residual
 
     # ---- default: rows sampled and reduced into the slots by one kernel (no rebatch tensors)
     def _slots_fused(self, query, value, reference_points_cam, bev_mask, spatial_shapes, level_start_index):
@@ -256,13 +269,13 @@ class SpatialCrossAttention(BaseModule):
             from .. import sharding
             query = sharding.sum_grad(query, self.process_group)
         # Linear(query) rows are the same for every camera that sees the pillar: once per pillar
-        offsets = da.sampling_offsets(query).view(bs, Q, H, L, P, 2)
-        logits = da.attention_weights(query).view(bs, Q, H, L * P)
+        offsets = _linear(da.sampling_offsets, query).view(bs, Q, H, L, P, 2)
+        logits = _linear(da.attention_weights, query).view(bs, Q, H, L * P)
         plan = sca.unit_plan(world, rank, cams)
         values = []
         for cam0, ncl, _, _, _ in plan:
             v = value[cam0:cam0 + ncl].permute(2, 0, 1, 3).reshape(bs * ncl, K, C)      # [bs*ncl, K, C], batch-major
-            values.append(da.value_proj(v).view(bs * ncl, K, H, C // H))
+            values.append(_linear(da.value_proj, v).view(bs * ncl, K, H, C // H))
         return sca.SCARowsFunction.apply(plan, bs, spatial_shapes, level_start_index, reference_points_cam,
                                          offsets, logits, idx, count, inv, *values)
 
@@ -353,7 +366,7 @@ class TemporalSelfAttention(BaseModule):
         H, L, P, Qn = self.num_heads, self.num_levels, self.num_points, self.num_bev_queue
 
         query = torch.cat([value[:bs], query], -1)
-        value = self.value_proj(value)
+        value = _linear(self.value_proj, value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.reshape(bs * Qn, num_value, H, -1)
@@ -376,7 +389,7 @@ class TemporalSelfAttention(BaseModule):
         output = msda_apply(value, spatial_shapes, level_start_index, loc, weights, self.im2col_step)
         # mean over the queue (:255-261): [bs*Qn, nq, C] -> [bs, nq, C]
         output = output.view(bs, Qn, num_query, embed_dims).mean(1)
-        output = self.output_proj(output)
+        output = _linear(self.output_proj, output)
         if not self.batch_first:
             output = output.permute(1, 0, 2)
         return self.dropout(output) + identity
@@ -428,7 +441,7 @@ class PredictionMSDeformableAttention(BaseModule):
         assert (spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum() == num_value
         H, L, P = self.num_heads, self.num_levels, self.num_points
 
-        value = self.value_proj(value)
+        value = _linear(self.value_proj, value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, H, -1)
@@ -444,7 +457,7 @@ class PredictionMSDeformableAttention(BaseModule):
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
 
         output = msda_apply(value, spatial_shapes, level_start_index, loc, weights, self.im2col_step)
-        output = self.output_proj(output)
+        output = _linear(self.output_proj, output)
         if not self.batch_first:
             output = output.permute(1, 0, 2)
         return self.dropout(output) + identity

@@ -38,6 +38,7 @@ import torch.nn.functional as F
 from . import bev_geometry, sca, sharding, synthetic
 from . import modules as _modules  # noqa: F401  (registers the attention classes)
 from .head import ViDARRayHead
+from .modules.deform_attn import _linear
 from .registry import build_attention
 
 PC_RANGE = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
@@ -127,7 +128,7 @@ class FFN(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return x + self.drop(self.fc2(self.drop(F.relu(self.fc1(x)))))
+        return x + self.drop(_linear(self.fc2, self.drop(F.relu(_linear(self.fc1, x)))))
 
 
 class LearnedPositionalEncoding(nn.Module):
