@@ -528,7 +528,7 @@ def run_ours(args, light=False):
                 "avg_launch_ms": parts[dom] / n_launch,
                 "note": "duration = CUDA events around the op in the timed region (incl. grad_value "
                         "zero-fill for bwd); gather traffic is served by L2, see DESIGN.md"}
-    cpu = cpu_baseline(sample_only=True)
+    cpu = cpu_baseline(sample_only=True) if world == 1 else {"note": "timed at N=1 only (rank 0), see the N=1 line"}
     line = {
         "metric": METRIC, "value": RAYS / (ms_step * 1e-3), "unit": "rays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
