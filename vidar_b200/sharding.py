@@ -176,15 +176,20 @@ def mark_partial(module):
 
 def allreduce_partial_grads(module, group):
     """Sum the gradients of every tagged parameter over `group` in ONE all-reduce."""
-    ps = [p for p in module.parameters() if getattr(p, "vidar_partial_grad", False) and p.grad is not None]
+    # every rank must contribute the SAME bucket: a rank that owns no camera never touches the backbone and has no
+    # gradient for it (None) -- it sends zeros and receives the sum
+    ps = [p for p in module.parameters() if getattr(p, "vidar_partial_grad", False) and p.requires_grad]
     if not ps or dist.get_world_size(group) == 1:
         return 0
-    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps])
     dist.all_reduce(flat, group=group)
     off = 0
     for p in ps:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off: off + n].view_as(p.grad))
+        n = p.numel()
+        if p.grad is None:
+            p.grad = flat[off: off + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[off: off + n].view_as(p.grad))
         off += n
     return flat.numel()
 
