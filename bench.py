@@ -505,8 +505,7 @@ def run_ours(args, light=False):
                   "H2D / compute / D2H on three streams"}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     # ---- roofline of the dominant kernel (msda_backward_kernel), this rank's launches
@@ -540,8 +539,7 @@ def run_ours(args, light=False):
         "msda_query_samples_per_s": NUM_CAMS * BEV_Q * HEADS * len(LEVELS) * POINTS / ((parts["msda_fwd"] + parts["msda_bwd"]) * 1e-3),
     }
     _emit(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
 
 
 def check_sharded(dev, rank, world, grp, last, groups, msda_stage, grad_bev, latent, embed, grad_embed, sigma, origin,
@@ -860,6 +858,16 @@ def run_pretrain(args):
             "stage_ms": agg, "loss": float(loss), "peak_mem_gb": peak_gb, "clocks": clocks, "gpu_launches": int(launches)}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _finish(world):
+    """End of a multi-rank run.  With a captured CUDA graph that contains NCCL kernels, tearing the process group
+    down (or the interpreter's exit handlers) was seen to hang for minutes AFTER the JSON line was out (8 and 4
+    ranks, gpurun r2h): every result is already written, so the ranks leave without running destructors."""
+    if world > 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _emit(line):
