@@ -125,3 +125,36 @@ def test_row_collectives_with_autograd(tmp_path, world):
         torch.testing.assert_close(got["gx"], xs[r].grad)
         torch.testing.assert_close(got["gw"], w.grad)
         torch.testing.assert_close(got["grep"], rep.grad)
+
+
+def _partial_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lin_a, lin_b = torch.nn.Linear(3, 2).double(), torch.nn.Linear(3, 2).double()
+    with torch.no_grad():
+        for m in (lin_a, lin_b):
+            m.weight.fill_(0.5)
+            m.bias.zero_()
+    model = torch.nn.ModuleList([lin_a, lin_b])
+    sharding.mark_partial(model)
+    x = torch.full((4, 3), float(rank + 1), dtype=torch.float64)
+    # rank 0 uses both layers, every other rank only the second one (a rank that owns no camera never runs the backbone)
+    y = lin_b(x).sum() + (lin_a(x).sum() if rank == 0 else 0.0)
+    y.backward()
+    assert (lin_a.weight.grad is None) == (rank != 0)
+    sharding.allreduce_partial_grads(model, dist.group.WORLD)
+    torch.save(dict(ga=lin_a.weight.grad, gb=lin_b.weight.grad), os.path.join(tmp, f"pg{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_partial_grad_bucket_is_identical_on_ranks_without_a_gradient(tmp_path):
+    """A tagged parameter that one rank never used (grad None) still takes part in the bucketed all-reduce
+    (that rank sends zeros) and ends up with the summed gradient everywhere."""
+    world = 3
+    mp.spawn(_partial_worker, args=(world, 29900 + os.getpid() % 90, str(tmp_path)), nprocs=world, join=True)
+    ga = torch.full((2, 3), 4.0 * 1, dtype=torch.float64)                      # only rank 0: sum over 4 rows of x = 1
+    gb = torch.full((2, 3), 4.0 * (1 + 2 + 3), dtype=torch.float64)
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), f"pg{r}.pt"), weights_only=False)
+        torch.testing.assert_close(got["ga"], ga)
+        torch.testing.assert_close(got["gb"], gb)
