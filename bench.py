@@ -865,6 +865,11 @@ def _finish(world):
     down (or the interpreter's exit handlers) was seen to hang for minutes AFTER the JSON line was out (8 and 4
     ranks, gpurun r2h): every result is already written, so the ranks leave without running destructors."""
     if world > 1:
+        import torch.distributed as dist
+        # nobody leaves before rank 0 has written the line (a rank that disappears early could be noticed by the
+        # peers' NCCL watchdog); the barrier is an ordinary collective, which is not what hung
+        dist.barrier()
+        torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)

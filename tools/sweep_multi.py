@@ -45,8 +45,7 @@ def main():
             out["configs"].append(r)
     if rank == 0:
         os.write(bench._REAL_STDOUT, (json.dumps(out, indent=1) + "\n").encode())
-    if torch.distributed.is_initialized():
-        torch.distributed.destroy_process_group()
+    bench._finish(a.gpus)      # multi-rank: leave without process-group teardown (see bench._finish)
 
 
 if __name__ == "__main__":
