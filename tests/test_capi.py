@@ -75,3 +75,36 @@ def test_argument_validation_of_the_fused_entry_points():
     # zero rows is a valid no-op
     assert L.vidar_latent_proj_out_forward(N, N, N, N, N, 0, 256, 16, 16, N) == 0
     assert L.vidar_ray_gumbel_forward(*((N,) * 8 + (0, 1, 4, 4, 4, 8, 1.0, N))) == 0
+
+
+def test_argument_validation_of_the_round2_entry_points():
+    """Row-indirect MSDA (BEV-slot) ops, the visible-list compaction and the tcgen05 Linear: size contracts are
+    rejected with a message before any launch.  Pointers are only compared with NULL on these paths, so a dummy
+    non-null address stands in for device memory (every call here fails validation; nothing is launched)."""
+    L = _lib.lib()
+    N, X = None, ctypes.c_void_p(0x1000)
+    rows_fwd = lambda **k: (X, X, X, X, X, k.get("idx", X), X, X, k.get("slots", X), k.get("bs", 1), k.get("ncl", 6),
+                            k.get("cam0", 0), 100, 8, k.get("C", 32), 4, k.get("rows", 50), k.get("Qd", 50), 8,
+                            k.get("S", 1), k.get("lo", 0), k.get("hi", 1), N)
+    cases = [
+        (L.vidar_msda_rows_forward, (N,) * 9 + (1, 6, 0, 100, 8, 32, 4, 50, 50, 8, 1, 0, 1, N), b"null pointer"),
+        (L.vidar_msda_rows_forward, rows_fwd(rows=60), b"exceed the pillar count"),
+        (L.vidar_msda_rows_forward, rows_fwd(idx=N, rows=40), b"without an index list"),
+        (L.vidar_msda_rows_forward, rows_fwd(S=4, lo=3, hi=5), b"bad sub-slice"),
+        (L.vidar_msda_rows_forward, rows_fwd(C=24), b"head dim must be 16, 32 or 64"),
+        (L.vidar_msda_rows_forward, rows_fwd(cam0=-1), b"bad sizes"),
+        (L.vidar_msda_rows_forward, rows_fwd(slots=N), b"null output"),
+        (L.vidar_msda_rows_backward, (X,) * 9 + (N, X, X, 1, 6, 0, 100, 8, 32, 4, 50, 50, 8, 1, 0, 1, N), b"null gradient pointer"),
+        (L.vidar_msda_sca_rows_forward, (X, X, X, N, X, X, X, X, X, X, 1, 6, 0, 100, 8, 32, 4, 50, 50, 8, 4, 1, 0, 1, N), b"null reference points"),
+        (L.vidar_sca_compact, (N, N, N, N, 6, 1, 100, 4, N), b"null pointer"),
+        (L.vidar_sca_compact, (X, X, X, X, 6, 1, 0, 4, N), b"bad sizes"),
+        (L.vidar_linear_tf32x3, (N, N, N, N, N, 10, 128, 128, N), b"null pointer"),
+        (L.vidar_linear_tf32x3, (X, X, X, X, X, 10, 128, 100, N), b"in_features must be a multiple of 32"),
+        (L.vidar_linear_tf32x3, (X, X, X, X, X, 10, 96, 128, N), b"out_features of 128"),
+        (L.vidar_linear_tf32x3, (X, X, X, X, X, 0, 128, 128, N), b"bad sizes"),
+        (L.vidar_linear_tf32x3, (ctypes.c_void_p(0x1004), X, X, X, X, 10, 128, 128, N), b"16-byte aligned"),
+    ]
+    for fn, args, needle in cases:
+        rc = fn(*args)
+        assert rc == 1, (fn.__name__, rc, L.vidar_last_error())
+        assert needle in L.vidar_last_error(), (fn.__name__, L.vidar_last_error())
