@@ -742,7 +742,8 @@ def run_reference(args):
         return
     arm = CpuArm()
     # the sampled steps stay within ~2 minutes; one honest full-size step is measured after them
-    r = arm.run(args.steps, args.warmup, budget_s=110.0, full_step=os.environ.get("VIDAR_REF_FULL_STEP", "1") == "1")
+    r = arm.run(args.steps, args.warmup, budget_s=float(os.environ.get("VIDAR_REF_BUDGET_S", "110")),
+                full_step=os.environ.get("VIDAR_REF_FULL_STEP", "1") == "1")
     t = float(np.mean(r["t"]))
     value = r["f"] * RAYS / t
     sample = arm.describe(r)
