@@ -39,7 +39,8 @@ def _sources():
 
 def _digest():
     h = hashlib.sha256()
-    files = _sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "vidar_b200.h")]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]      # every included header
+    files = _sources() + headers + [os.path.join(ROOT, "include", "vidar_b200.h")]
     for f in sorted(files):
         with open(f, "rb") as fh:
             h.update(os.path.relpath(f, ROOT).encode())      # machine-independent
