@@ -112,3 +112,32 @@ def test_unit_plan_partitions_every_row_exactly_once():
             assert plan_cameras(plan) == sorted(plan_cameras(plan))
         assert len(seen) == cams * nblk
         assert max(sizes) - min(sizes) < 1e-9
+
+
+def test_shared_camera_groups_cannot_deadlock():
+    """A camera split over several ranks gets its own sub-communicator (features broadcast, grad_value summed
+    inside it).  Ranks enqueue these small collectives in whatever order autograd reaches them, so the scheme is
+    only safe if no cyclic wait is possible: the graph "ranks joined by a shared camera" must be a forest and
+    two ranks must never share more than one camera."""
+    from vidar_b200.sca import camera_ranks, plan_cameras, unit_plan
+    cams = 6
+    for world in range(1, 13):
+        owners = camera_ranks(world, cams)
+        assert sorted(owners) == list(range(cams)) and all(owners[c] for c in owners)
+        for rank in range(world):                     # camera_ranks is the inverse of the per-rank plans
+            assert [c for c in owners if rank in owners[c]] == plan_cameras(unit_plan(world, rank, cams))
+        shared = [tuple(m) for m in owners.values() if len(m) > 1]
+        pairs = [frozenset((a, b)) for m in shared for i, a in enumerate(m) for b in m[i + 1:]]
+        assert len(pairs) == len(set(pairs)), f"world {world}: two ranks share two cameras"
+        parent = list(range(world))                   # union-find: an edge inside one component would close a cycle
+
+        def find(x):
+            while parent[x] != x:
+                parent[x] = parent[parent[x]]
+                x = parent[x]
+            return x
+        for m in shared:
+            roots = {find(r) for r in m}
+            assert len(roots) == len(m), f"world {world}: cyclic wait possible through camera group {m}"
+            for r in m[1:]:
+                parent[find(r)] = find(m[0])
