@@ -802,7 +802,8 @@ def run_pretrain(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         grp = dist.group.WORLD
-    model, opt = pretrain.build(dev, grp)
+    row_sharded = bool(getattr(args, "row_sharded", False)) and world > 1
+    model, opt = pretrain.build(dev, grp, row_sharded=row_sharded)
     eager = args.impl == "reference"
     if eager:
         _eager_reference_ops()
@@ -854,7 +855,9 @@ def run_pretrain(args):
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (cuDNN convolutions may use TF32, as in the reference's default PyTorch settings)",
             "data": "synthetic (N(0,1) frames, nuScenes-like 6-camera rig, LiDAR-like rays)", "samples_per_s": 1e3 / ms,
             "config": {"workload": PRETRAIN_WORKLOAD, "ops": "eager reference formulas (MSDA, LatentRendering core)" if eager else "vidar_b200 CUDA ops",
-                       "sharding": "one sample over all ranks: cameras (backbone, SCA) and BEV rows (SCA output, LatentRendering) sharded, rest replicated" if world > 1 else "single GPU"},
+                       "sharding": ("single GPU" if world == 1 else
+                                    "one sample over all ranks: cameras (backbone, SCA) and BEV rows (SCA output, LatentRendering) sharded, rest replicated"
+                                    + ("; encoder row-wise stages (TSA, norms, FFN) on the rank's BEV rows" if row_sharded else ""))},
             "impl": "reference (eager torch formulas of the two hot paths, same GPU)" if eager else "ours",
             "stage_ms": agg, "loss": float(loss), "peak_mem_gb": peak_gb, "clocks": clocks, "gpu_launches": int(launches)}))
     if world > 1:
@@ -896,6 +899,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the timed steps eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--row-sharded", dest="row_sharded", action="store_true",
+                    help="--workload pretrain, N > 1: TSA / norms / FFN of the encoder on the rank's BEV rows (EncoderLayer.forward_rows)")
     ap.add_argument("--workload", default="hotpath", choices=["hotpath", "pretrain"],
                     help="hotpath: BASELINE configs[1]+[2] (the headline line); pretrain: configs[3], the synthetic ViDAR-RN101 step "
                          "(--impl reference there = the same graph with the reference's eager torch formulas for MSDA / LatentRendering, on the GPU)")

@@ -229,14 +229,28 @@ class SpatialCrossAttention(BaseModule):
 
     def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, reference_points_cam=None,
-                bev_mask=None, level_start_index=None, flag="encoder", **kwargs):
+                bev_mask=None, level_start_index=None, flag="encoder", rows_out=False, summed_query_grad=False,
+                **kwargs):
+        """Sharded extras (not in the reference): `rows_out=True` returns only this rank's block of BEV rows
+        (`sharding.row_range` of the bs*Q flattened rows; `residual` must then hold those rows) and skips the
+        all-gather -- for row-wise consumers (LayerNorm, FFN, `LatentRendering.forward_rows`);
+        `summed_query_grad=True` says the caller already sums the query's per-rank partial gradient (it came out of
+        `sharding.all_gather_rows(..., grad="sum")`), so no all-reduce is added here."""
         if key is None:
             key = query
         if value is None:
             value = key
+        world, _ = self._world()
+        if rows_out and (world == 1 or residual is None):
+            raise RuntimeError("rows_out needs a process group with more than one rank and the residual rows")
         inp_residual = query if residual is None else residual
         if query_pos is not None:
             query = query + query_pos
+        if world > 1 and not summed_query_grad:
+            # every rank samples only its cameras: the gradient that reaches the (replicated) query through
+            # offsets / logits is a per-rank partial sum -> one all-reduce of the 41 MB BEV-query gradient
+            from .. import sharding
+            query = sharding.sum_grad(query, self.process_group)
         if self._fusable(query, value, reference_points_cam):
             slots = self._slots_fused(query, value, reference_points_cam, bev_mask, spatial_shapes, level_start_index)
         else:
@@ -244,12 +258,13 @@ class SpatialCrossAttention(BaseModule):
                 raise RuntimeError("camera sharding needs the fused SpatialCrossAttention path "
                                    "(MSDeformableAttention3D with num_levels * num_points == 32, fp32, CUDA)")
             slots = self._slots_rebatch(query, key, value, reference_points_cam, bev_mask, spatial_shapes, level_start_index)
-        world, _ = self._world()
         if world > 1:
             from .. import sharding
             bs, Q, C = slots.shape
             rows = sharding.reduce_scatter_rows(slots.reshape(bs * Q, C), self.process_group)     # this rank's pillars
             rows = self.dropout(_linear(self.output_proj, rows))
+            if rows_out:
+                return rows + inp_residual.reshape(-1, C)
             full = sharding.all_gather_rows(rows, bs * Q, self.process_group).view(bs, Q, C)       # the BEV grid
             return full + inp_residual          # the residual stays replicated (its gradient is the full one)
         return self.dropout(_linear(self.output_proj, slots)) + inp_residual
@@ -263,11 +278,6 @@ class SpatialCrossAttention(BaseModule):
         H, L, P = da.num_heads, da.num_levels, da.num_points
         idx, count, inv = sca.compact_visible(bev_mask)
         world, rank = self._world()
-        if world > 1:
-            # every rank samples only its cameras: the gradient that reaches the (replicated) query through
-            # offsets / logits is a per-rank partial sum -> one all-reduce of the 41 MB BEV-query gradient
-            from .. import sharding
-            query = sharding.sum_grad(query, self.process_group)
         # Linear(query) rows are the same for every camera that sees the pillar: once per pillar
         offsets = _linear(da.sampling_offsets, query).view(bs, Q, H, L, P, 2)
         logits = _linear(da.attention_weights, query).view(bs, Q, H, L * P)
@@ -348,7 +358,12 @@ class TemporalSelfAttention(BaseModule):
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 key_padding_mask=None, reference_points=None, spatial_shapes=None,
-                level_start_index=None, flag="decoder", **kwargs):
+                level_start_index=None, flag="decoder", row_range=None, **kwargs):
+        """`row_range=(lo, hi)` (not in the reference; SURVEY.md 8e "TSA shards by query rows with the value
+        replicated"): `query`, `identity`, `query_pos` and `reference_points` hold only BEV rows lo..hi-1, `value`
+        is the full [bs*2, num_value, C] stack; the result is those rows of the full call."""
+        if row_range is not None and (value is None or not self.batch_first):
+            raise RuntimeError("row_range needs batch_first=True and an explicit full `value` stack")
         if value is None:
             assert self.batch_first
             bs, len_bev, c = query.shape
@@ -365,7 +380,10 @@ class TemporalSelfAttention(BaseModule):
         assert self.num_bev_queue == 2
         H, L, P, Qn = self.num_heads, self.num_levels, self.num_points, self.num_bev_queue
 
-        query = torch.cat([value[:bs], query], -1)
+        prev_rows = value[:bs] if row_range is None else value[:bs, row_range[0]:row_range[1]]
+        if prev_rows.shape[1] != num_query:
+            raise RuntimeError(f"{num_query} query rows but {prev_rows.shape[1]} rows of the previous BEV (row_range={row_range})")
+        query = torch.cat([prev_rows, query], -1)
         value = _linear(self.value_proj, value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)

@@ -171,6 +171,31 @@ class EncoderLayer(nn.Module):
             query = self.latent_render(query.view(bs, self.bev_hw[0], self.bev_hw[1], c)).view(bs, n, c)
         return self.norms[2](self.ffn(query))
 
+    def forward_rows(self, x_full, feats, bev_pos, ref_2d, prev_bev, shapes, lsi, ref_cam, bev_mask, bev_shapes, bev_lsi,
+                     group, last):
+        """The same layer with the BEV rows sharded over `group` (TSA / FFN / norms on the rank's rows,
+        value replicated; bs = 1).  `x_full` [1, Q, C] is the replicated layer input; every row-wise stage runs on
+        this rank's block only; the full grid is assembled twice: after the first norm (SpatialCrossAttention needs
+        every pillar's offsets for its cameras) and at the end (the next layer's TSA samples the whole BEV).  Both
+        all-gathers feed sharded consumers, so their backward is a reduce-scatter of partial gradients -- except the
+        last layer's, whose consumers (decoder, head) are replicated."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        bs, Q, C = x_full.shape
+        lo, hi = sharding.row_range(Q, rank, world)
+        q = self.self_attn(x_full[:, lo:hi], prev_bev, prev_bev, None, query_pos=bev_pos[:, lo:hi],
+                           reference_points=ref_2d[:, lo:hi], spatial_shapes=bev_shapes, level_start_index=bev_lsi,
+                           row_range=(lo, hi))
+        q = self.norms[0](q)                                                       # [1, rows, C]
+        q_full = sharding.all_gather_rows(q[0], Q, group, grad="sum")[None]
+        q = self.cross_attn(q_full, feats, feats, q, reference_points_cam=ref_cam, bev_mask=bev_mask,
+                            spatial_shapes=shapes, level_start_index=lsi, rows_out=True, summed_query_grad=True)
+        q = self.norms[1](q)                                                       # [rows, C]
+        if self.latent_render is not None:
+            q = self.latent_render.forward_rows(q, bs, self.bev_hw[0], self.bev_hw[1])
+        q = self.norms[2](self.ffn(q))
+        return sharding.all_gather_rows(q, Q, group, grad="slice" if last else "sum")[None]
+
 
 class DecoderLayer(nn.Module):
     """PredictionTransformerLayer (vidar_decoder.py:104-280) without latent rendering (the shipped
@@ -223,12 +248,17 @@ class SyntheticViDAR(nn.Module):
                                      use_dense_loss=True, loss_weight=[[1.0]] * (1 + future_frames))
         self.per_frame_loss_weight = (0.1, 0.1, 0.1, 1.0, 1.0)
         self.process_group = None
+        self.row_sharded = False
         self.timings = None
 
     # ---- sharding ------------------------------------------------------------------------------
-    def set_process_group(self, group):
+    def set_process_group(self, group, row_sharded=False):
+        """Shard one sample over `group`: cameras (backbone, SpatialCrossAttention), cells (LatentRendering).
+        `row_sharded=True` additionally runs every row-wise stage of the encoder (TSA, norms, FFN) on the rank's
+        block of BEV rows (`EncoderLayer.forward_rows`; bs = 1, rows divisible by the group size)."""
         import torch.distributed as dist
         self.process_group = group
+        self.row_sharded = bool(row_sharded) and group is not None and dist.get_world_size(group) > 1
         world = dist.get_world_size(group) if group is not None else 1
         rank = dist.get_rank(group) if group is not None else 0
         self.plan = sca.unit_plan(world, rank, self.num_cams)
@@ -246,6 +276,10 @@ class SyntheticViDAR(nn.Module):
                 sharding.mark_partial(m)
             self.cams_embeds.vidar_partial_grad = True
             self.level_embeds.vidar_partial_grad = True
+        for layer in self.encoder:      # row-wise stages see only this rank's rows: partial parameter gradients
+            for m in (layer.self_attn, layer.norms, layer.ffn):
+                for p_ in m.parameters():
+                    p_.vidar_partial_grad = self.row_sharded
         return self
 
     def _mark(self, name):
@@ -306,9 +340,22 @@ class SyntheticViDAR(nn.Module):
         hybrid = torch.stack([ref_2d, ref_2d], 1).reshape(bs * 2, Q, 1, 2)          # can_bus zeros: no ego shift
         bev_shapes = torch.tensor([[BEV_H, BEV_W]], device=dev)
         bev_lsi = torch.tensor([0], device=dev)
-        for layer in self.encoder:
+        rows_mode = getattr(self, "row_sharded", False)
+        if rows_mode:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.process_group)
+            if bs != 1 or Q % world != 0:
+                raise RuntimeError(f"row-sharded encoder: needs bs == 1 and BEV rows ({Q}) divisible by the group size ({world})")
+            # replicated tensors consumed by sharded stages: their gradients are per-rank partial sums
+            query = sharding.sum_grad(query, self.process_group)
+            bev_pos = sharding.sum_grad(bev_pos, self.process_group)
+        for i, layer in enumerate(self.encoder):
             pv = torch.stack([prev_bev if prev_bev is not None else query, query], 1).reshape(bs * 2, Q, EMBED)
-            query = layer(query, feats, bev_pos, hybrid, pv, spatial_shapes, lsi, ref_cam, bev_mask, bev_shapes, bev_lsi)
+            if rows_mode:
+                query = layer.forward_rows(query, feats, bev_pos, hybrid, pv, spatial_shapes, lsi, ref_cam, bev_mask,
+                                           bev_shapes, bev_lsi, self.process_group, last=i == len(self.encoder) - 1)
+            else:
+                query = layer(query, feats, bev_pos, hybrid, pv, spatial_shapes, lsi, ref_cam, bev_mask, bev_shapes, bev_lsi)
         return query
 
     # ---- future decoder (vidar_head_base.py:125-173) ----
@@ -430,10 +477,10 @@ def train_step(model, optimizer, sample, group=None, record=False):
     return loss.detach(), stages
 
 
-def build(device, group=None, lr=2e-4, seed=0, **model_kwargs):
+def build(device, group=None, lr=2e-4, seed=0, row_sharded=False, **model_kwargs):
     torch.manual_seed(seed)
     model = SyntheticViDAR(**model_kwargs).to(device)
-    model.set_process_group(group)
+    model.set_process_group(group, row_sharded=row_sharded)
     model.train()
     for m in model.modules():                      # dropout off: replicated parts must stay identical over ranks
         if isinstance(m, nn.Dropout):

@@ -76,7 +76,9 @@ def gather_rows(local_rows, world, total_rows, group=None):
 #   reduce_scatter_rows : partial sums [R, C] on every rank  ->  this rank's rows of the total
 #                         (backward: all-gather of the row gradients -- d total / d partial_r = I)
 #   all_gather_rows     : this rank's rows  ->  the full replicated tensor  (the ONE all-gather of the BEV
-#                         grid; backward: the local slice of the replicated gradient, no communication)
+#                         grid; backward: the local slice of the replicated gradient, no communication -- or,
+#                         with grad="sum", the reduce-scatter of per-rank partial gradients when the consumers
+#                         of the gathered grid are themselves sharded)
 # Parameters used on sharded data (value_proj on a rank's cameras, output_proj / FFN on a rank's rows)
 # end up with PARTIAL gradients; they are tagged with `mark_partial` and summed over the group once per
 # step by `allreduce_partial_grads` (one bucketed all-reduce, like DDP's).
@@ -85,62 +87,79 @@ def _rows_padded(n, world):
     return -(-n // world)
 
 
+def _reduce_scatter_block(partial, group):
+    """[R, ...] partial sums -> (this rank's block of the sum, rows per block)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    R = partial.shape[0]
+    per = _rows_padded(R, world)
+    x = partial.contiguous()
+    if per * world != R:
+        pad = x.new_zeros((per * world,) + tuple(x.shape[1:]))
+        pad[:R] = x
+        x = pad
+    lo = rank * per
+    if dist.get_backend(group) == "gloo":          # CPU tests: gloo has no reduce_scatter
+        x = x.clone()
+        dist.all_reduce(x, group=group)
+        out = x[lo: lo + per]
+    else:
+        out = x.new_empty((per,) + tuple(x.shape[1:]))
+        dist.reduce_scatter_tensor(out, x, group=group)
+    return out[: max(0, min(R, lo + per) - lo)], per
+
+
+def _all_gather_blocks(rows, R, group):
+    """This rank's block (possibly short) -> the full [R, ...] tensor."""
+    world = dist.get_world_size(group)
+    per = _rows_padded(R, world)
+    x = rows.contiguous()
+    if x.shape[0] != per:
+        pad = x.new_zeros((per,) + tuple(x.shape[1:]))
+        pad[: x.shape[0]] = x
+        x = pad
+    full = x.new_empty((per * world,) + tuple(x.shape[1:]))
+    dist.all_gather_into_tensor(full, x, group=group)
+    return full[:R]
+
+
 class _ReduceScatterRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, partial, group):
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        R = partial.shape[0]
-        per = _rows_padded(R, world)
-        x = partial.contiguous()
-        if per * world != R:
-            pad = x.new_zeros((per * world,) + tuple(x.shape[1:]))
-            pad[:R] = x
-            x = pad
-        lo = rank * per
-        if dist.get_backend(group) == "gloo":          # CPU tests: gloo has no reduce_scatter
-            x = x.clone()
-            dist.all_reduce(x, group=group)
-            out = x[lo: lo + per]
-        else:
-            out = x.new_empty((per,) + tuple(x.shape[1:]))
-            dist.reduce_scatter_tensor(out, x, group=group)
-        n = max(0, min(R, lo + per) - lo)
-        ctx.meta = (group, R, per, world)
-        return out[:n]
+        ctx.meta = (group, partial.shape[0])
+        return _reduce_scatter_block(partial, group)[0]
 
     @staticmethod
     def backward(ctx, grad_rows):
-        group, R, per, world = ctx.meta
-        g = grad_rows.contiguous()
-        if g.shape[0] != per:
-            pad = g.new_zeros((per,) + tuple(g.shape[1:]))
-            pad[: g.shape[0]] = g
-            g = pad
-        full = g.new_empty((per * world,) + tuple(g.shape[1:]))
-        dist.all_gather_into_tensor(full, g, group=group)
-        return full[:R], None
+        group, R = ctx.meta
+        return _all_gather_blocks(grad_rows, R, group), None
 
 
 class _AllGatherRows(torch.autograd.Function):
+    """Consumers downstream are REPLICATED: every rank holds the same full gradient, its block is a slice."""
+
     @staticmethod
     def forward(ctx, rows, R, group):
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        per = _rows_padded(R, world)
-        x = rows.contiguous()
-        if x.shape[0] != per:
-            pad = x.new_zeros((per,) + tuple(x.shape[1:]))
-            pad[: x.shape[0]] = x
-            x = pad
-        full = x.new_empty((per * world,) + tuple(x.shape[1:]))
-        dist.all_gather_into_tensor(full, x, group=group)
-        lo = rank * per
-        ctx.meta = (lo, max(0, min(R, lo + per) - lo))
-        return full[:R]
+        ctx.meta = row_range(R, dist.get_rank(group), dist.get_world_size(group))
+        return _all_gather_blocks(rows, R, group)
 
     @staticmethod
     def backward(ctx, grad_full):
-        lo, n = ctx.meta
-        return grad_full[lo: lo + n], None, None
+        lo, hi = ctx.meta
+        return grad_full[lo:hi], None, None
+
+
+class _AllGatherRowsSumGrad(torch.autograd.Function):
+    """Consumers downstream are SHARDED (each rank uses the gathered tensor for its own rows / cameras only): the
+    per-rank gradients are partial sums, the block's gradient is their reduce-scatter."""
+
+    @staticmethod
+    def forward(ctx, rows, R, group):
+        ctx.group = group
+        return _all_gather_blocks(rows, R, group)
+
+    @staticmethod
+    def backward(ctx, grad_full):
+        return _reduce_scatter_block(grad_full, ctx.group)[0], None, None
 
 
 def row_range(R, rank, world):
@@ -156,9 +175,14 @@ def reduce_scatter_rows(partial, group):
     return _ReduceScatterRows.apply(partial, group)
 
 
-def all_gather_rows(rows, R, group):
-    """This rank's block of rows -> the full [R, ...] tensor on every rank."""
-    return _AllGatherRows.apply(rows, R, group)
+def all_gather_rows(rows, R, group, grad="slice"):
+    """This rank's block of rows -> the full [R, ...] tensor on every rank.
+    grad="slice": what follows is replicated computation (identical gradients on every rank; backward takes the
+    block, no communication).  grad="sum": what follows is sharded computation (row-sharded encoder layers, camera-
+    sharded sampling) whose per-rank gradients are partial sums; backward reduce-scatters them."""
+    if grad not in ("slice", "sum"):
+        raise ValueError(f"grad must be 'slice' or 'sum', got {grad!r}")
+    return (_AllGatherRows if grad == "slice" else _AllGatherRowsSumGrad).apply(rows, R, group)
 
 
 def local_rows(full, group):
