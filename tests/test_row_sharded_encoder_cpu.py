@@ -122,3 +122,64 @@ def test_row_sharded_encoder_layers_equal_plain_layers(tmp_path):
             assert g is not None, n
             torch.testing.assert_close(g, p.grad, rtol=1e-4, atol=2e-5 * float(p.grad.abs().max()) + 1e-9,
                                        msg=lambda m: f"rank {rank} param {n}: {m}")
+
+
+# ---- decoder stack: two future frames chained through `run_decoder`, every layer output also read by a replicated head
+def _decoder_layers():
+    from vidar_b200.pretrain import DecoderLayer
+    torch.manual_seed(21)
+    layers = torch.nn.ModuleList([DecoderLayer() for _ in range(2)])
+    g = torch.Generator().manual_seed(22)
+    with torch.no_grad():
+        for p in layers.parameters():
+            if p.dim() > 1:
+                p.copy_(torch.randn(p.shape, generator=g) / p.shape[-1] ** 0.5)
+    return layers.eval()
+
+
+def _run_decoder(layers, d, group):
+    from vidar_b200 import pretrain
+    q0, pos, prev0 = (d[k].clone().requires_grad_(True) for k in ("x", "pos", "prev"))
+    head = torch.nn.Linear(q0.shape[-1], 8)
+    with torch.no_grad():
+        head.weight.copy_(torch.linspace(-1, 1, head.weight.numel()).view_as(head.weight))
+        head.bias.zero_()
+    ref = d["ref_2d"][:1]
+    loss, prev = 0.0, prev0
+    for frame in range(2):
+        inter, last = pretrain.run_decoder(layers, q0, prev, pos, ref, d["bev_shapes"], d["bev_lsi"], group)
+        loss = loss + (head(inter) * (frame + 1)).square().mean()          # replicated consumer of every layer output
+        prev = last + 0.5                                                   # next frame's previous BEV
+    (loss + (last * d["gout"]).sum()).backward()
+    return loss.detach(), q0.grad, pos.grad, prev0.grad, head.weight.grad
+
+
+def _decoder_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vidar_b200 import sharding
+    _patch_oracle()
+    layers, d = _decoder_layers(), _inputs()
+    sharding.mark_partial(layers)
+    res = _run_decoder(layers, d, dist.group.WORLD)
+    sharding.allreduce_partial_grads(layers, dist.group.WORLD)
+    torch.save(dict(res=res, params={n: p.grad for n, p in layers.named_parameters()}), f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_decoder_stack_equals_plain_stack(tmp_path):
+    world = 2
+    out = str(tmp_path / "dec.pt")
+    mp.spawn(_decoder_worker, args=(world, 29450 + os.getpid() % 300, out), nprocs=world, join=True)
+    _patch_oracle()
+    layers, d = _decoder_layers(), _inputs()
+    want = _run_decoder(layers, d, None)
+    names = ("loss", "grad_query", "grad_pos", "grad_prev", "grad_head_weight")
+    for rank in range(world):
+        got = torch.load(f"{out}.{rank}", weights_only=False)
+        for k, a, w in zip(names, got["res"], want):
+            torch.testing.assert_close(a, w, rtol=1e-4, atol=1e-5 * float(w.abs().max()) + 1e-9, msg=lambda m: f"rank {rank} {k}: {m}")
+        for n, p in layers.named_parameters():
+            torch.testing.assert_close(got["params"][n], p.grad, rtol=1e-4, atol=2e-5 * float(p.grad.abs().max()) + 1e-9,
+                                       msg=lambda m: f"rank {rank} param {n}: {m}")

@@ -217,6 +217,41 @@ class DecoderLayer(nn.Module):
         query = self.norms[1](query)
         return self.norms[2](self.ffn(query))
 
+    def forward_rows(self, x_full, prev_feats, bev_pos, tgt_points, ref_points, bev_shapes, bev_lsi, group):
+        """The same layer on this rank's block of BEV rows (bs = 1): both attentions sample replicated values (the full
+        query grid / the previous BEV) for the rank's rows, norms and FFN are row-wise, ONE all-gather returns the grid
+        (backward: reduce-scatter -- `prev_feats` and `bev_pos` must come through `sharding.sum_grad`, replicated
+        consumers of the result through `sharding.replicated_view`)."""
+        import torch.distributed as dist
+        Q = x_full.shape[1]
+        lo, hi = sharding.row_range(Q, dist.get_rank(group), dist.get_world_size(group))
+        pos = bev_pos[:, lo:hi]
+        q = self.self_attn(x_full[:, lo:hi], None, x_full, None, query_pos=pos, reference_points=tgt_points[:, lo:hi],
+                           spatial_shapes=bev_shapes, level_start_index=bev_lsi)
+        q = self.norms[0](q)
+        q = self.cross_attn(q, prev_feats, prev_feats, None, query_pos=pos, reference_points=ref_points[:, lo:hi],
+                            spatial_shapes=bev_shapes, level_start_index=bev_lsi)
+        q = self.norms[2](self.ffn(self.norms[1](q)))
+        return sharding.all_gather_rows(q[0], Q, group, grad="sum")[None]
+
+
+def run_decoder(layers, query, prev, bev_pos, ref, bev_shapes, bev_lsi, group=None):
+    """The future-BEV decoder stack -> (outputs of every layer stacked [inter, bs, Q, C] for the head, last output for
+    the next future frame).  `group`: row-sharded layers (`DecoderLayer.forward_rows`); the stacked outputs are then
+    (like the returned last output) views for replicated consumers (`sharding.replicated_view`)."""
+    inter = []
+    if group is None:
+        for layer in layers:
+            query = layer(query, prev, bev_pos, ref, ref, bev_shapes, bev_lsi)
+            inter.append(query)
+        return torch.stack(inter), inter[-1]
+    query, prev, bev_pos = (sharding.sum_grad(t, group) for t in (query, prev, bev_pos))
+    for layer in layers:
+        query = layer.forward_rows(query, prev, bev_pos, ref, ref, bev_shapes, bev_lsi, group)
+        inter.append(sharding.replicated_view(query, group))
+    # the caller's use of the last output (next frame's `prev`, which passes through sum_grad again) is replicated too
+    return torch.stack(inter), inter[-1]
+
 
 class SyntheticViDAR(nn.Module):
     """The pre-training graph of ViDAR-RN101 (3 history frames, 3 future frames, 5 predicted head frames)."""
@@ -280,6 +315,8 @@ class SyntheticViDAR(nn.Module):
             for m in (layer.self_attn, layer.norms, layer.ffn):
                 for p_ in m.parameters():
                     p_.vidar_partial_grad = self.row_sharded
+        for p_ in self.decoder.parameters():
+            p_.vidar_partial_grad = self.row_sharded
         return self
 
     def _mark(self, name):
@@ -369,11 +406,11 @@ class SyntheticViDAR(nn.Module):
         ref = bev_geometry.get_reference_points(BEV_H, BEV_W, dim="2d", bs=bs, device=dev)      # identity ego motion
         bev_shapes = torch.tensor([[BEV_H, BEV_W]], device=dev)
         bev_lsi = torch.tensor([0], device=dev)
-        inter = []
-        for layer in self.decoder:
-            query = layer(query, prev, bev_pos, ref, ref, bev_shapes, bev_lsi)
-            inter.append(query)
-        return torch.stack(inter)                                                     # [inter, bs, Q, C]
+        rows_mode = getattr(self, "row_sharded", False)
+        if rows_mode and (bs != 1 or query.shape[1] % torch.distributed.get_world_size(self.process_group) != 0):
+            raise RuntimeError("row-sharded decoder: needs bs == 1 and BEV rows divisible by the group size")
+        # -> ([inter, bs, Q, C] for the head, the last layer's output for the next future frame)
+        return run_decoder(self.decoder, query, prev, bev_pos, ref, bev_shapes, bev_lsi, self.process_group if rows_mode else None)
 
     def forward_head(self, next_bev_feats):
         """vidar_head_v1.py:64-92: [frames, inter, bs, Q, C] -> [frames, inter, pred_frame, bs, Q, heights]."""
@@ -411,9 +448,9 @@ class SyntheticViDAR(nn.Module):
         next_bev_feats = [ref_bev.unsqueeze(0).repeat(inter_num, 1, 1, 1)]
         prev_bev_input = ref_bev.unsqueeze(1)
         for _ in range(self.future_frames):
-            pred_feat = self.decode_future(prev_bev_input, can_bus)
+            pred_feat, last = self.decode_future(prev_bev_input, can_bus)
             next_bev_feats.append(pred_feat)
-            prev_bev_input = pred_feat[-1].unsqueeze(1)                                # queue length 1 (vidar.py:359-360)
+            prev_bev_input = last.unsqueeze(1)                                         # queue length 1 (vidar.py:359-360)
         self._mark("future_decoder")
         next_bev_feats = torch.stack(next_bev_feats, 0)
         next_bev_preds = self.forward_head(next_bev_feats)                              # [F, inter, pred_frame, bs, Q, 16]

@@ -236,3 +236,21 @@ class _SumGrad(torch.autograd.Function):
 
 def sum_grad(x, group):
     return _SumGrad.apply(x, group)
+
+
+class _ScaleGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.scale, None
+
+
+def replicated_view(x, group):
+    """View of a tensor gathered with `all_gather_rows(..., grad="sum")` for a REPLICATED consumer (one that every
+    rank runs identically): its gradient is the same on every rank, so each rank contributes 1/world of it to the
+    reduce-scatter.  Lets one gathered tensor feed sharded and replicated consumers at once."""
+    return _ScaleGrad.apply(x, 1.0 / dist.get_world_size(group))
