@@ -38,8 +38,13 @@ def _worker(rank, world, port, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from vidar_b200 import pretrain, sharding
     res = []
-    for group in (None, dist.group.WORLD):
-        model, opt = pretrain.build(dev, group, seed=1, **SMALL)
+    modes = [(None, False), (dist.group.WORLD, False)]
+    if os.environ.get("VIDAR_TEST_ROW_SHARDED") == "1":
+        # opt-in: the row-sharded encoder / decoder was built after the round's GPU budget was spent; its host logic is
+        # held to the single-process graph over gloo (tests/test_pretrain_sharding_cpu.py), it has not run on a GPU yet
+        modes.append((dist.group.WORLD, True))
+    for group, row_sharded in modes:
+        model, opt = pretrain.build(dev, group, seed=1, row_sharded=row_sharded, **SMALL)
         sample = pretrain.synthetic_sample(dev, **SAMPLE)
         opt.zero_grad(set_to_none=True)
         losses = model.forward_train(sample["img"], sample["lidar2img"], sample["gt_points"])
@@ -60,9 +65,10 @@ def test_sharded_step_equals_single_gpu(tmp_path):
         pytest.skip("needs 2 GPUs")
     out = str(tmp_path / "p.pt")
     mp.spawn(_worker, args=(2, 29840 + os.getpid() % 100, out), nprocs=2, join=True)
-    (l1, g1), (l2, g2) = torch.load(out, weights_only=False)
-    assert abs(l1 - l2) <= 1e-4 * abs(l1)
-    assert set(g1) == set(g2)
-    for n in g1:
-        scale = float(g1[n].abs().max())
-        torch.testing.assert_close(g2[n], g1[n], rtol=2e-3, atol=2e-4 * scale + 1e-9, msg=lambda m: f"{n}: {m}")
+    (l1, g1), *sharded = torch.load(out, weights_only=False)
+    for l2, g2 in sharded:
+        assert abs(l1 - l2) <= 1e-4 * abs(l1)
+        assert set(g1) == set(g2)
+        for n in g1:
+            scale = float(g1[n].abs().max())
+            torch.testing.assert_close(g2[n], g1[n], rtol=2e-3, atol=2e-4 * scale + 1e-9, msg=lambda m: f"{n}: {m}")
