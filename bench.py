@@ -872,6 +872,9 @@ def _finish(world):
         import torch.distributed as dist
         # nobody leaves before rank 0 has written the line (a rank that disappears early could be noticed by the
         # peers' NCCL watchdog); the barrier is an ordinary collective, which is not what hung
+        guard = threading.Timer(30.0, lambda: os._exit(0))      # every result is out: never wait on teardown for long
+        guard.daemon = True
+        guard.start()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
