@@ -108,3 +108,23 @@ def test_argument_validation_of_the_round2_entry_points():
         rc = fn(*args)
         assert rc == 1, (fn.__name__, rc, L.vidar_last_error())
         assert needle in L.vidar_last_error(), (fn.__name__, L.vidar_last_error())
+
+
+def test_python_call_sites_pass_as_many_arguments_as_the_header_declares():
+    """Static: every `<lib>.vidar_xxx(...)` call in the package, bench, tools and tests passes the number of
+    arguments `include/vidar_b200.h` declares (ctypes would only notice at run time, on the GPU box)."""
+    import ast
+    import glob
+    decl = {n: len(a) for n, a in _lib.declared_symbols()}
+    seen, bad = 0, []
+    files = [p for pat in ("vidar_b200/**/*.py", "tests/*.py", "tools/*.py", "*.py") for p in glob.glob(os.path.join(ROOT, pat), recursive=True)]
+    for path in files:
+        with open(path) as fh:
+            tree = ast.parse(fh.read())
+        for n in ast.walk(tree):
+            if (isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr in decl
+                    and not any(isinstance(a, ast.Starred) for a in n.args) and not n.keywords):
+                seen += 1
+                if len(n.args) != decl[n.func.attr]:
+                    bad.append(f"{os.path.relpath(path, ROOT)}:{n.lineno} {n.func.attr}: {len(n.args)} args, header says {decl[n.func.attr]}")
+    assert seen >= 30 and not bad, "\n".join(bad)
