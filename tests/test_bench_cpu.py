@@ -40,3 +40,26 @@ def test_gpu_arm_refuses_to_run_without_a_device():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert p.returncode != 0 and p.stdout.strip() == "" and "no CPU fallback" in p.stderr
+
+
+def test_multi_rank_exit_leaves_after_the_line_without_teardown(tmp_path):
+    """bench._finish: every rank passes one barrier after rank 0's line and leaves with status 0 without running
+    process-group destructors (2 gloo ranks here; the CUDA synchronize is a no-op on this host)."""
+    code = (
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "torch.cuda.synchronize = lambda *a, **k: None\n"
+        "dist.init_process_group('gloo')\n"
+        "if dist.get_rank() == 0:\n"
+        "    bench._emit('{\"ok\": true}')\n"
+        "bench._finish(dist.get_world_size())\n"
+        "print('not reached')\n")
+    port = 29900 + os.getpid() % 90
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert [p.returncode for p in procs] == [0, 0], outs
+    assert outs[0][0].strip() == '{"ok": true}' and outs[1][0].strip() == ""
