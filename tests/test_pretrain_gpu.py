@@ -37,6 +37,10 @@ def _worker(rank, world, port, out):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from vidar_b200 import pretrain, sharding
+    # the comparison is about the sharding logic: keep the convolutions in fp32 (TF32 results depend on the algorithm
+    # cuDNN picks, which depends on how many cameras a rank batches)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     res = []
     modes = [(None, False), (dist.group.WORLD, False)]
     if os.environ.get("VIDAR_TEST_ROW_SHARDED") == "1":
